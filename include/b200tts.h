@@ -1,0 +1,141 @@
+/*
+ * b200tts.h -- C ABI of libb200tts.so: the sm_100a replacement for the hot paths of
+ * lturing/tacotronv2_wavernn_chinese.
+ *
+ * The reference is pure Python and has no FFI of its own; the
+ * boundary that a maintainer binds is therefore the body of three Python methods.
+ * Each entry point below names the reference interface it replaces
+ * (paths relative to the reference root):
+ *
+ *   b200tts_wavernn_create     <- WaveRNN.__init__ + WaveRNN.load      wavernn/models/fatchord_version.py:93-129, :414-417
+ *   b200tts_wavernn_upsample   <- UpsampleNetwork.forward (+pad_tensor) wavernn/models/fatchord_version.py:82-89, :185-186, :281-291
+ *   b200tts_wavernn_generate   <- WaveRNN.generate (unbatched branch)   wavernn/models/fatchord_version.py:169-264
+ *                                 incl. decode_mu_law                   wavernn/utils/dsp.py:98-103
+ *   b200tts_wavernn_generate_host  same, HOST buffers in/out (what wavernn_gen.py:41 sees end to end)
+ *   b200tts_wavernn_fold / _xfade  <- fold_with_overlap / xfade_and_unfold  fatchord_version.py:293-405 (opt-in --batched)
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in any signature (`stream` is a cudaStream_t passed as void*).
+ *   - all `d_*` pointers are DEVICE pointers on the context's device, all `h_*` pointers are HOST pointers;
+ *     the caller owns every buffer it passes, the library owns only what *_create allocates.
+ *   - every function returns 0 on success or a negative B200TTS_E* code; the message is available from
+ *     b200tts_last_error() (thread local).  Nothing aborts or throws across the ABI.
+ *   - work is enqueued on `stream` and is asynchronous unless stated; a context is bound to one device and
+ *     its calls must be serialised by the caller (one context per GPU per process).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with B200TTS_ECUDA.
+ */
+#ifndef B200TTS_H_
+#define B200TTS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200TTS_ABI_VERSION 1
+
+enum {
+  B200TTS_OK = 0,
+  B200TTS_EINVAL = -1,   /* bad argument / unsupported configuration            */
+  B200TTS_ECUDA = -2,    /* CUDA runtime error (message carries the CUDA string) */
+  B200TTS_ENOMEM = -3,   /* device or host allocation failed                    */
+  B200TTS_EMISSING = -4, /* a required weight tensor was not supplied           */
+  B200TTS_ESHAPE = -5    /* a weight tensor has the wrong shape                 */
+};
+
+/* Model dimensions = the constructor arguments of the reference WaveRNN (fatchord_version.py:93-95),
+ * filled from wavernn_hparams.py:18-41,50. */
+typedef struct {
+  int32_t rnn_dims;            /* voc_rnn_dims     512 */
+  int32_t fc_dims;             /* voc_fc_dims      512 */
+  int32_t bits;                /* bits             10  -> n_classes = 1 << bits */
+  int32_t pad;                 /* voc_pad          2   */
+  int32_t feat_dims;           /* num_mels         80  */
+  int32_t compute_dims;        /* voc_compute_dims 128 */
+  int32_t res_out_dims;        /* voc_res_out_dims 128 (aux_dims = res_out_dims / 4) */
+  int32_t res_blocks;          /* voc_res_blocks   10  */
+  int32_t n_upsample;          /* len(voc_upsample_factors), <= 4 */
+  int32_t upsample_factors[4]; /* (5, 5, 11) */
+  int32_t hop_length;          /* 275 == prod(upsample_factors) */
+} b200tts_wavernn_cfg;
+
+/* One named fp32 weight tensor in HOST memory, contiguous row-major; names are the reference
+ * state_dict keys ("I.weight", "rnn1.weight_ih_l0", "upsample.resnet.layers.3.batch_norm1.running_var", ...).
+ * The library copies and repacks; the caller may free the data after *_create returns. */
+typedef struct {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} b200tts_tensor;
+
+/* Sampling noise for `Categorical(softmax(logits)).sample()` (fatchord_version.py:232-235), which the
+ * reference evaluates as argmax_i(p_i / q_i), q_i ~ Exp(1).  The kernels evaluate the equivalent
+ * argmax_i(logit_i - log q_i). */
+enum {
+  B200TTS_RNG_PHILOX = 0,          /* q from Philox4x32-10 keyed by (seed, global utterance, step, class) */
+  B200TTS_RNG_EXT_EXPONENTIAL = 1  /* q read from d_q[S][B][n_classes] (tests: noise shared with the oracle) */
+};
+typedef struct {
+  int32_t mode;
+  uint64_t seed;
+  uint64_t utterance_offset; /* global index of row 0 (multi-GPU shards keep results independent of the split) */
+  const float* d_q;          /* EXT_EXPONENTIAL only */
+} b200tts_rng;
+
+enum {
+  B200TTS_KERNEL_AUTO = 0,
+  B200TTS_KERNEL_UTTERANCE = 1, /* one CTA per group of utterances, weights streamed from L2      */
+  B200TTS_KERNEL_GRID = 2       /* weight-stationary persistent cooperative grid, all SMs per step */
+};
+typedef struct {
+  int32_t kernel;             /* B200TTS_KERNEL_*                                                      */
+  int32_t mu_law;             /* hp.mu_law (wavernn_hparams.py:28); non-zero -> decode_mu_law          */
+  const int16_t* d_teacher;   /* optional [B][S]: fed back instead of the sampled label (teacher forcing) */
+  float* d_logits;            /* optional [S][B][n_classes]: fc3 outputs of every step (debug / parity) */
+  int32_t max_steps;          /* 0 = all S = T*hop steps; otherwise stop early (no wave is produced)   */
+} b200tts_gen_opts;
+
+typedef struct b200tts_wavernn b200tts_wavernn;
+
+int b200tts_abi_version(void);
+const char* b200tts_last_error(void);
+/* number of CUDA devices visible, or a negative error */
+int b200tts_device_count(void);
+
+int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b200tts_wavernn_cfg* cfg,
+                           const b200tts_tensor* weights, int n_weights);
+void b200tts_wavernn_destroy(b200tts_wavernn* ctx);
+
+/* d_mel [B][feat][T] (unpadded, as generate() receives it) ->
+ *   d_mels_up    [B][T*hop][feat]     (may be NULL)
+ *   d_aux_frames [B][T][res_out]      (may be NULL; aux is constant within a hop, so it is kept at frame rate)
+ *   d_aux_full   [B][T*hop][res_out]  (may be NULL; the reference's materialised layout) */
+int b200tts_wavernn_upsample(b200tts_wavernn* ctx, const float* d_mel, int B, int T, float* d_mels_up,
+                             float* d_aux_frames, float* d_aux_full, void* stream);
+
+/* d_mel [B][feat][T] -> d_labels [B][S] (S = T*hop, may be NULL), d_wave [B][(T-1)*hop] float64 mu-law decoded,
+ * truncated and faded exactly like fatchord_version.py:243-258 (may be NULL).  Needs T >= 21 when d_wave != NULL. */
+int b200tts_wavernn_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
+                             const b200tts_gen_opts* opts, int16_t* d_labels, double* d_wave, void* stream);
+
+/* Same with HOST buffers: copies h_mel to the device, generates, copies labels / wave back, synchronises. */
+int b200tts_wavernn_generate_host(b200tts_wavernn* ctx, const float* h_mel, int B, int T, const b200tts_rng* rng,
+                                  const b200tts_gen_opts* opts, int16_t* h_labels, double* h_wave);
+
+/* The Exp(1) noise the PHILOX mode uses for (utterance, step, class): d_q[n_steps][B][n_classes].
+ * Lets a test hand the production noise stream to the oracle. */
+int b200tts_philox_exponential(int device, uint64_t seed, uint64_t utterance_offset, int B, int step0, int n_steps,
+                               int n_classes, float* d_q, void* stream);
+
+/* Number of kernel launches the library has issued on this context since creation (bench.py: gpu_launches). */
+int64_t b200tts_wavernn_launch_count(const b200tts_wavernn* ctx);
+/* Milliseconds (CUDA events on the launch stream) spent in the per-sample generation kernel by the most recent
+ * generate call; blocks until that kernel has finished.  Negative on error. */
+double b200tts_wavernn_last_kernel_ms(b200tts_wavernn* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TTS_H_ */

@@ -1,0 +1,582 @@
+// libb200tts.so -- C-ABI entry points (include/b200tts.h), weight packing and launch logic.
+#include "../../include/b200tts.h"
+
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "wavernn_upsample.cuh"
+#include "wavernn_utt.cuh"
+
+using namespace b200tts;
+
+static thread_local std::string g_err;
+
+#define API_BEGIN try {
+#define API_END                                       \
+  }                                                   \
+  catch (const ::b200tts::Error& e) {                 \
+    g_err = e.what();                                 \
+    return e.code;                                    \
+  }                                                   \
+  catch (const std::bad_alloc&) {                     \
+    g_err = "host allocation failed";                 \
+    return B200TTS_ENOMEM;                            \
+  }                                                   \
+  catch (const std::exception& e) {                   \
+    g_err = e.what();                                 \
+    return B200TTS_EINVAL;                            \
+  }                                                   \
+  return B200TTS_OK;
+
+#define REQUIRE(cond, code, msg)                                 \
+  do {                                                           \
+    if (!(cond)) throw ::b200tts::Error((code), std::string(msg)); \
+  } while (0)
+
+namespace {
+
+struct DeviceBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    if (p) B200_CUDA(cudaFree(p));
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      throw Error(B200TTS_ENOMEM, std::string("cudaMalloc(") + std::to_string(n) + "): " + cudaGetErrorString(e));
+    }
+    bytes = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostPinned {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMallocHost(&p, n);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      throw Error(B200TTS_ENOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    }
+    bytes = n;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    B200_CUDA(cudaGetDevice(&prev));
+    if (prev != dev) B200_CUDA(cudaSetDevice(dev));
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+using TensorMap = std::map<std::string, const b200tts_tensor*>;
+
+const b200tts_tensor* need(const TensorMap& m, const std::string& name, std::initializer_list<int64_t> shape) {
+  auto it = m.find(name);
+  if (it == m.end()) throw Error(B200TTS_EMISSING, "missing weight tensor '" + name + "'");
+  const b200tts_tensor* t = it->second;
+  size_t nd = shape.size();
+  bool ok = (size_t)t->ndim == nd && t->data != nullptr;
+  size_t i = 0;
+  for (int64_t s : shape) {
+    if (ok && t->shape[i] != s) ok = false;
+    ++i;
+  }
+  if (!ok) {
+    std::string got = "[";
+    for (int k = 0; k < t->ndim && k < 4; ++k) got += (k ? "," : "") + std::to_string(t->shape[k]);
+    got += "]";
+    std::string want = "[";
+    i = 0;
+    for (int64_t s : shape) want += (i++ ? "," : "") + std::to_string(s);
+    want += "]";
+    throw Error(B200TTS_ESHAPE, "weight '" + name + "' has shape " + got + ", expected " + want);
+  }
+  return t;
+}
+
+// Host-side staging of one packed fp32 blob; every sub-array starts 16-byte aligned.
+struct Packer {
+  std::vector<float> h;
+  size_t add(size_t n) {
+    size_t off = (h.size() + 3) & ~size_t(3);
+    h.resize(off + n, 0.f);
+    return off;
+  }
+};
+
+inline int round4(int x) { return (x + 3) & ~3; }
+
+}  // namespace
+
+struct b200tts_wavernn {
+  int device = 0;
+  b200tts_wavernn_cfg cfg{};
+  int aux = 0, NC = 0, NT = 0, sm_count = 0;
+  DeviceBuf weights;          // packed blob
+  StepWeights sw{};
+  ResnetParams rp{};
+  const float* d_fir = nullptr;   // [hop][NT]
+  // scratch
+  DeviceBuf mels_up, aux_frames, labels, mel_in, wave, grid_scratch;
+  HostPinned h_stage;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int64_t launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200tts_abi_version(void) { return B200TTS_ABI_VERSION; }
+extern "C" const char* b200tts_last_error(void) { return g_err.c_str(); }
+extern "C" int b200tts_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return B200TTS_ECUDA;
+  }
+  return n;
+}
+
+// Composite polyphase FIR of the Stretch2d/Conv2d chain (see wavernn_upsample.cuh).  Returns [hop][NT] doubles.
+static std::vector<double> composite_fir(const b200tts_wavernn_cfg& c, const std::vector<std::vector<double>>& taps,
+                                         int* NT_out) {
+  const int hop = c.hop_length;
+  // reach of the composite response beyond the frame's own box, in output samples
+  int reach = 0, rate = hop;
+  for (int j = 0; j < c.n_upsample; ++j) {
+    rate /= c.upsample_factors[j];
+    reach += c.upsample_factors[j] * rate;
+  }
+  int side = (reach + hop - 1) / hop;            // frames on each side that can contribute
+  int NT = 2 * side + 1;
+  REQUIRE(NT <= kMaxTaps, B200TTS_EINVAL, "upsample factors give a composite FIR wider than kMaxTaps frames");
+  const int nf = 2 * side + 5, f0 = nf / 2;      // impulse in the middle, far from both ends
+  std::vector<double> x(nf, 0.0);
+  x[f0] = 1.0;
+  for (int j = 0; j < c.n_upsample; ++j) {
+    const int s = c.upsample_factors[j];
+    std::vector<double> r(x.size() * s);
+    for (size_t i = 0; i < r.size(); ++i) r[i] = x[i / s];
+    std::vector<double> y(r.size(), 0.0);
+    for (long i = 0; i < (long)r.size(); ++i) {
+      double a = 0.0;
+      for (int k = 0; k < 2 * s + 1; ++k) {
+        long idx = i + k - s;
+        if (idx >= 0 && idx < (long)r.size()) a += taps[j][k] * r[idx];
+      }
+      y[i] = a;
+    }
+    x.swap(y);
+  }
+  // out[n] = sum_f melpad[f] * Rsp[n - hop*f];  with n = hop*fr + ph and f = fr + (j - side):  Rsp[ph - hop*(j-side)]
+  std::vector<double> fir((size_t)hop * NT);
+  for (int ph = 0; ph < hop; ++ph)
+    for (int j = 0; j < NT; ++j) {
+      long idx = (long)hop * f0 + ph - (long)hop * (j - side);
+      fir[(size_t)ph * NT + j] = (idx >= 0 && idx < (long)x.size()) ? x[idx] : 0.0;
+    }
+  *NT_out = NT;
+  return fir;
+}
+
+extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b200tts_wavernn_cfg* cfg,
+                                      const b200tts_tensor* weights, int n_weights) {
+  API_BEGIN
+  REQUIRE(out && cfg && weights && n_weights > 0, B200TTS_EINVAL, "null argument");
+  *out = nullptr;
+  const b200tts_wavernn_cfg& c = *cfg;
+  REQUIRE(c.n_upsample >= 1 && c.n_upsample <= 4, B200TTS_EINVAL, "n_upsample must be 1..4");
+  int prod = 1;
+  for (int j = 0; j < c.n_upsample; ++j) {
+    REQUIRE(c.upsample_factors[j] >= 1, B200TTS_EINVAL, "bad upsample factor");
+    prod *= c.upsample_factors[j];
+  }
+  REQUIRE(prod == c.hop_length, B200TTS_EINVAL, "prod(upsample_factors) != hop_length (wavernn_train.py:67 asserts the same)");
+  REQUIRE(c.res_out_dims % 4 == 0, B200TTS_EINVAL, "res_out_dims must be divisible by 4");
+  REQUIRE(c.rnn_dims % 128 == 0 && c.fc_dims % 128 == 0, B200TTS_EINVAL, "rnn_dims / fc_dims must be multiples of 128");
+  REQUIRE(c.bits >= 2 && c.bits <= 15, B200TTS_EINVAL, "bits must be 2..15 (labels are int16)");
+  REQUIRE(c.compute_dims <= 1024 && c.res_out_dims <= 1024, B200TTS_EINVAL, "compute/res_out dims too large");
+  const int R = c.rnn_dims, F = c.fc_dims, AUX = c.res_out_dims / 4, FEAT = c.feat_dims, NC = 1 << c.bits;
+  const int C = c.compute_dims, O = c.res_out_dims, K = 2 * c.pad + 1;
+  REQUIRE(AUX % 4 == 0, B200TTS_EINVAL, "aux dims (res_out_dims/4) must be a multiple of 4");
+  int ndev = 0;
+  B200_CUDA(cudaGetDeviceCount(&ndev));
+  REQUIRE(device >= 0 && device < ndev, B200TTS_EINVAL, "no such CUDA device");
+  DeviceGuard dg(device);
+
+  TensorMap tm;
+  for (int i = 0; i < n_weights; ++i)
+    if (weights[i].name) tm[weights[i].name] = &weights[i];
+
+  auto ctx = new b200tts_wavernn();
+  struct Cleanup {
+    b200tts_wavernn* c;
+    ~Cleanup() {
+      if (c) b200tts_wavernn_destroy(c);
+    }
+  } cleanup{ctx};
+  ctx->device = device;
+  ctx->cfg = c;
+  ctx->aux = AUX;
+  ctx->NC = NC;
+  B200_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+
+  Packer pk;
+  // ---- step weights, original layouts ----
+  const int nin = 1 + FEAT + AUX, ldI = round4(nin);
+  const float* Iw = need(tm, "I.weight", {R, nin})->data;
+  size_t oI = pk.add((size_t)R * ldI);
+  for (int r = 0; r < R; ++r) std::memcpy(&pk.h[oI + (size_t)r * ldI], Iw + (size_t)r * nin, sizeof(float) * nin);
+  auto copy = [&](const std::string& name, std::initializer_list<int64_t> shape) {
+    const b200tts_tensor* t = need(tm, name, shape);
+    size_t n = 1;
+    for (int64_t s : shape) n *= (size_t)s;
+    size_t off = pk.add(n);
+    std::memcpy(&pk.h[off], t->data, n * sizeof(float));
+    return off;
+  };
+  size_t oIb = copy("I.bias", {R});
+  size_t o_ih1 = copy("rnn1.weight_ih_l0", {3 * R, R}), o_hh1 = copy("rnn1.weight_hh_l0", {3 * R, R});
+  size_t o_bih1 = copy("rnn1.bias_ih_l0", {3 * R}), o_bhh1 = copy("rnn1.bias_hh_l0", {3 * R});
+  size_t o_ih2 = copy("rnn2.weight_ih_l0", {3 * R, R + AUX}), o_hh2 = copy("rnn2.weight_hh_l0", {3 * R, R});
+  size_t o_bih2 = copy("rnn2.bias_ih_l0", {3 * R}), o_bhh2 = copy("rnn2.bias_hh_l0", {3 * R});
+  size_t o_fc1 = copy("fc1.weight", {F, R + AUX}), o_fc1b = copy("fc1.bias", {F});
+  size_t o_fc2 = copy("fc2.weight", {F, F + AUX}), o_fc2b = copy("fc2.bias", {F});
+  size_t o_fc3 = copy("fc3.weight", {NC, F}), o_fc3b = copy("fc3.bias", {NC});
+
+  // ---- MelResNet, transposed to [in][out]; BatchNorm (eval, eps 1e-5) folded to scale/shift in double ----
+  const float* cin = need(tm, "upsample.resnet.conv_in.weight", {C, FEAT, K})->data;
+  size_t o_cin = pk.add((size_t)FEAT * K * C);
+  for (int cc = 0; cc < C; ++cc)
+    for (int i = 0; i < FEAT; ++i)
+      for (int j = 0; j < K; ++j) pk.h[o_cin + ((size_t)i * K + j) * C + cc] = cin[((size_t)cc * FEAT + i) * K + j];
+  const int nbn = 1 + 2 * c.res_blocks;
+  size_t o_bns = pk.add((size_t)nbn * C), o_bnh = pk.add((size_t)nbn * C);
+  auto fold_bn = [&](const std::string& prefix, int slot) {
+    const float* g = need(tm, prefix + ".weight", {C})->data;
+    const float* b = need(tm, prefix + ".bias", {C})->data;
+    const float* m = need(tm, prefix + ".running_mean", {C})->data;
+    const float* v = need(tm, prefix + ".running_var", {C})->data;
+    for (int cc = 0; cc < C; ++cc) {
+      double sc = (double)g[cc] / std::sqrt((double)v[cc] + 1e-5);
+      pk.h[o_bns + (size_t)slot * C + cc] = (float)sc;
+      pk.h[o_bnh + (size_t)slot * C + cc] = (float)((double)b[cc] - (double)m[cc] * sc);
+    }
+  };
+  fold_bn("upsample.resnet.batch_norm", 0);
+  size_t o_res = pk.add((size_t)c.res_blocks * 2 * C * C);
+  for (int blk = 0; blk < c.res_blocks; ++blk) {
+    std::string p = "upsample.resnet.layers." + std::to_string(blk);
+    for (int h = 0; h < 2; ++h) {
+      const float* w = need(tm, p + (h ? ".conv2.weight" : ".conv1.weight"), {C, C, 1})->data;
+      size_t base = o_res + ((size_t)blk * 2 + h) * C * C;
+      for (int co = 0; co < C; ++co)
+        for (int ci = 0; ci < C; ++ci) pk.h[base + (size_t)ci * C + co] = w[(size_t)co * C + ci];
+    }
+    fold_bn(p + ".batch_norm1", 1 + 2 * blk);
+    fold_bn(p + ".batch_norm2", 2 + 2 * blk);
+  }
+  const float* cow = need(tm, "upsample.resnet.conv_out.weight", {O, C, 1})->data;
+  size_t o_cout = pk.add((size_t)C * O);
+  for (int o = 0; o < O; ++o)
+    for (int ci = 0; ci < C; ++ci) pk.h[o_cout + (size_t)ci * O + o] = cow[(size_t)o * C + ci];
+  size_t o_coutb = copy("upsample.resnet.conv_out.bias", {O});
+
+  // ---- composite FIR ----
+  std::vector<std::vector<double>> taps(c.n_upsample);
+  for (int j = 0; j < c.n_upsample; ++j) {
+    int s = c.upsample_factors[j];
+    const float* w = need(tm, "upsample.up_layers." + std::to_string(2 * j + 1) + ".weight", {1, 1, 1, 2 * s + 1})->data;
+    taps[j].assign(w, w + 2 * s + 1);
+  }
+  int NT = 0;
+  std::vector<double> fir = composite_fir(c, taps, &NT);
+  ctx->NT = NT;
+  size_t o_fir = pk.add(fir.size());
+  for (size_t i = 0; i < fir.size(); ++i) pk.h[o_fir + i] = (float)fir[i];
+
+  ctx->weights.ensure(pk.h.size() * sizeof(float));
+  B200_CUDA(cudaMemcpy(ctx->weights.p, pk.h.data(), pk.h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  const float* base = ctx->weights.as<float>();
+  StepWeights& sw = ctx->sw;
+  sw.I_w = base + oI; sw.I_b = base + oIb;
+  sw.ih1_w = base + o_ih1; sw.hh1_w = base + o_hh1; sw.ih1_b = base + o_bih1; sw.hh1_b = base + o_bhh1;
+  sw.ih2_w = base + o_ih2; sw.hh2_w = base + o_hh2; sw.ih2_b = base + o_bih2; sw.hh2_b = base + o_bhh2;
+  sw.fc1_w = base + o_fc1; sw.fc1_b = base + o_fc1b; sw.fc2_w = base + o_fc2; sw.fc2_b = base + o_fc2b;
+  sw.fc3_w = base + o_fc3; sw.fc3_b = base + o_fc3b;
+  sw.R = R; sw.F = F; sw.aux = AUX; sw.feat = FEAT; sw.NC = NC; sw.ldI = ldI;
+  ResnetParams& rp = ctx->rp;
+  rp.conv_in_t = base + o_cin; rp.bn_scale = base + o_bns; rp.bn_shift = base + o_bnh; rp.res_w_t = base + o_res;
+  rp.conv_out_t = base + o_cout; rp.conv_out_b = base + o_coutb;
+  rp.feat = FEAT; rp.k = K; rp.C = C; rp.O = O; rp.blocks = c.res_blocks; rp.pad = c.pad;
+  ctx->d_fir = base + o_fir;
+
+  B200_CUDA(cudaEventCreate(&ctx->ev0));
+  B200_CUDA(cudaEventCreate(&ctx->ev1));
+  cleanup.c = nullptr;
+  *out = ctx;
+  API_END
+}
+
+extern "C" void b200tts_wavernn_destroy(b200tts_wavernn* ctx) {
+  if (!ctx) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(ctx->device);
+  ctx->weights.release();
+  ctx->mels_up.release();
+  ctx->aux_frames.release();
+  ctx->labels.release();
+  ctx->mel_in.release();
+  ctx->wave.release();
+  ctx->grid_scratch.release();
+  ctx->h_stage.release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (prev >= 0) cudaSetDevice(prev);
+  delete ctx;
+}
+
+extern "C" int64_t b200tts_wavernn_launch_count(const b200tts_wavernn* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" double b200tts_wavernn_last_kernel_ms(b200tts_wavernn* ctx) {
+  if (!ctx || !ctx->ev_valid) {
+    g_err = "no generate call has been timed on this context";
+    return -1.0;
+  }
+  float ms = 0.f;
+  cudaError_t e = cudaEventSynchronize(ctx->ev1);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  if (e != cudaSuccess) {
+    g_err = std::string("cudaEventElapsedTime: ") + cudaGetErrorString(e);
+    return -1.0;
+  }
+  return (double)ms;
+}
+
+// ---- conditioning ---------------------------------------------------------------------------------
+static void run_upsample(b200tts_wavernn* ctx, const float* d_mel, int B, int T, float* d_mels_up, float* d_aux_frames,
+                         float* d_aux_full, cudaStream_t st) {
+  const b200tts_wavernn_cfg& c = ctx->cfg;
+  const int hop = c.hop_length, O = c.res_out_dims;
+  float* auxf = d_aux_frames;
+  if (!auxf && d_aux_full) {
+    ctx->aux_frames.ensure((size_t)B * T * O * sizeof(float));
+    auxf = ctx->aux_frames.as<float>();
+  }
+  if (auxf) {
+    constexpr int FT = 8;
+    int threads = ((std::max(c.compute_dims, 32) + 31) / 32) * 32;
+    size_t smem = ((size_t)c.feat_dims * (2 * c.pad + 1) * FT + 2 * (size_t)c.compute_dims * FT) * sizeof(float);
+    if (smem > 48 * 1024)
+      B200_CUDA(cudaFuncSetAttribute(melresnet_kernel<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((T + FT - 1) / FT, B);
+    melresnet_kernel<FT><<<grid, threads, smem, st>>>(ctx->rp, d_mel, T, auxf);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (d_mels_up) {
+    size_t n = (size_t)T * hop * c.feat_dims;
+    dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 4096), B);
+    mel_fir_kernel<<<grid, 256, 0, st>>>(d_mel, ctx->d_fir, T, c.feat_dims, hop, c.pad, ctx->NT, d_mels_up);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (d_aux_full) {
+    size_t n = (size_t)T * hop * O;
+    dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 4096), B);
+    aux_repeat_kernel<<<grid, 256, 0, st>>>(auxf, T, hop, O, d_aux_full);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+}
+
+extern "C" int b200tts_wavernn_upsample(b200tts_wavernn* ctx, const float* d_mel, int B, int T, float* d_mels_up,
+                                        float* d_aux_frames, float* d_aux_full, void* stream) {
+  API_BEGIN
+  REQUIRE(ctx && d_mel, B200TTS_EINVAL, "null argument");
+  REQUIRE(B >= 1 && T >= 1, B200TTS_EINVAL, "B and T must be positive");
+  REQUIRE(B <= 65535, B200TTS_EINVAL, "B must be <= 65535");
+  DeviceGuard dg(ctx->device);
+  run_upsample(ctx, d_mel, B, T, d_mels_up, d_aux_frames, d_aux_full, (cudaStream_t)stream);
+  API_END
+}
+
+// ---- generation -----------------------------------------------------------------------------------
+template <int G>
+static void launch_utt(b200tts_wavernn* ctx, const GenArgs& a, cudaStream_t st) {
+  const StepWeights& w = ctx->sw;
+  size_t fl = (size_t)G * (w.ldI + w.R + 4 * w.R + 2 * (w.R + w.aux) + (w.F + w.aux) + w.F + w.NC);
+  size_t smem = fl * sizeof(float);
+  REQUIRE(smem <= 227 * 1024, B200TTS_EINVAL, "model too large for the utterance kernel's shared memory");
+  B200_CUDA(cudaFuncSetAttribute(wavernn_utt_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (a.B + G - 1) / G;
+  wavernn_utt_kernel<G><<<grid, kUttThreads, smem, st>>>(w, a);
+  B200_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
+                         const b200tts_gen_opts* opts, int16_t* d_labels, double* d_wave, cudaStream_t st) {
+  const b200tts_wavernn_cfg& c = ctx->cfg;
+  const int hop = c.hop_length, S = T * hop, O = c.res_out_dims;
+  b200tts_gen_opts o{};
+  if (opts) o = *opts;
+  else o.mu_law = 1;
+  b200tts_rng r{};
+  if (rng) r = *rng;
+  REQUIRE(r.mode == B200TTS_RNG_PHILOX || r.mode == B200TTS_RNG_EXT_EXPONENTIAL, B200TTS_EINVAL, "unknown rng mode");
+  REQUIRE(r.mode != B200TTS_RNG_EXT_EXPONENTIAL || r.d_q, B200TTS_EINVAL, "EXT_EXPONENTIAL needs d_q");
+  REQUIRE(o.max_steps >= 0 && o.max_steps <= S, B200TTS_EINVAL, "max_steps out of range");
+  const int steps = o.max_steps ? o.max_steps : S;
+  const int fade_len = 20 * hop;                      // fatchord_version.py:256
+  const int wave_len = (T - 1) * hop;                 // :184
+  if (d_wave) {
+    REQUIRE(steps == S, B200TTS_EINVAL, "a wave needs all steps (max_steps must be 0)");
+    REQUIRE(wave_len >= fade_len, B200TTS_EINVAL,
+            "T must be >= 21 frames: the reference's 20-hop fade-out (fatchord_version.py:256-258) fails below that");
+  }
+  ctx->mels_up.ensure((size_t)B * S * c.feat_dims * sizeof(float));
+  ctx->aux_frames.ensure((size_t)B * T * O * sizeof(float));
+  int16_t* labels = d_labels;
+  if (!labels) {
+    ctx->labels.ensure((size_t)B * S * sizeof(int16_t));
+    labels = ctx->labels.as<int16_t>();
+  }
+  run_upsample(ctx, d_mel, B, T, ctx->mels_up.as<float>(), ctx->aux_frames.as<float>(), nullptr, st);
+
+  GenArgs a{};
+  a.mels_up = ctx->mels_up.as<float>();
+  a.aux_frames = ctx->aux_frames.as<float>();
+  a.B = B; a.S = S; a.T = T; a.hop = hop; a.steps = steps;
+  a.rng_mode = r.mode; a.seed = r.seed; a.utt_offset = r.utterance_offset; a.q = r.d_q;
+  a.teacher = o.d_teacher; a.logits_out = o.d_logits; a.labels = labels;
+
+  int kernel = o.kernel;
+  if (kernel == B200TTS_KERNEL_AUTO) kernel = B200TTS_KERNEL_UTTERANCE;
+  B200_CUDA(cudaEventRecord(ctx->ev0, st));
+  if (kernel == B200TTS_KERNEL_UTTERANCE) {
+    // utterances per CTA: enough CTAs to cover the SMs first, then amortise the L2 weight stream over more rows
+    int per = (B + ctx->sm_count - 1) / ctx->sm_count;
+    if (per <= 1) launch_utt<1>(ctx, a, st);
+    else if (per <= 2) launch_utt<2>(ctx, a, st);
+    else if (per <= 4) launch_utt<4>(ctx, a, st);
+    else launch_utt<8>(ctx, a, st);
+  } else {
+    throw Error(B200TTS_EINVAL, "unknown kernel selector");
+  }
+  B200_CUDA(cudaEventRecord(ctx->ev1, st));
+  ctx->ev_valid = true;
+  if (d_wave) {
+    dim3 grid((wave_len + 255) / 256, B);
+    finish_wave_kernel<<<grid, 256, 0, st>>>(labels, S, wave_len, fade_len, ctx->NC, o.mu_law, d_wave);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+}
+
+extern "C" int b200tts_wavernn_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
+                                        const b200tts_gen_opts* opts, int16_t* d_labels, double* d_wave, void* stream) {
+  API_BEGIN
+  REQUIRE(ctx && d_mel, B200TTS_EINVAL, "null argument");
+  REQUIRE(B >= 1 && T >= 1 && B <= 65535, B200TTS_EINVAL, "B must be 1..65535 and T positive");
+  DeviceGuard dg(ctx->device);
+  run_generate(ctx, d_mel, B, T, rng, opts, d_labels, d_wave, (cudaStream_t)stream);
+  API_END
+}
+
+extern "C" int b200tts_wavernn_generate_host(b200tts_wavernn* ctx, const float* h_mel, int B, int T, const b200tts_rng* rng,
+                                             const b200tts_gen_opts* opts, int16_t* h_labels, double* h_wave) {
+  API_BEGIN
+  REQUIRE(ctx && h_mel, B200TTS_EINVAL, "null argument");
+  REQUIRE(B >= 1 && T >= 1 && B <= 65535, B200TTS_EINVAL, "B must be 1..65535 and T positive");
+  REQUIRE(!opts || (!opts->d_teacher && !opts->d_logits), B200TTS_EINVAL, "device-side debug buffers need the device entry point");
+  REQUIRE(!rng || rng->mode == B200TTS_RNG_PHILOX, B200TTS_EINVAL, "the host entry point only takes the PHILOX mode");
+  DeviceGuard dg(ctx->device);
+  const b200tts_wavernn_cfg& c = ctx->cfg;
+  const size_t S = (size_t)T * c.hop_length, wave_len = (size_t)(T - 1) * c.hop_length;
+  const size_t mel_bytes = (size_t)B * c.feat_dims * T * sizeof(float);
+  const size_t lab_bytes = (size_t)B * S * sizeof(int16_t), wav_bytes = (size_t)B * wave_len * sizeof(double);
+  cudaStream_t st = nullptr;   // legacy default stream: ordered with everything else the caller enqueued
+  ctx->mel_in.ensure(mel_bytes);
+  ctx->h_stage.ensure(std::max(mel_bytes, std::max(lab_bytes, wav_bytes)));
+  std::memcpy(ctx->h_stage.p, h_mel, mel_bytes);
+  B200_CUDA(cudaMemcpyAsync(ctx->mel_in.p, ctx->h_stage.p, mel_bytes, cudaMemcpyHostToDevice, st));
+  ctx->labels.ensure(lab_bytes);
+  double* d_wave = nullptr;
+  if (h_wave) {
+    ctx->wave.ensure(wav_bytes);
+    d_wave = ctx->wave.as<double>();
+  }
+  run_generate(ctx, ctx->mel_in.as<float>(), B, T, rng, opts, ctx->labels.as<int16_t>(), d_wave, st);
+  if (h_labels) {
+    B200_CUDA(cudaMemcpyAsync(ctx->h_stage.p, ctx->labels.p, lab_bytes, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(h_labels, ctx->h_stage.p, lab_bytes);
+  }
+  if (h_wave) {
+    B200_CUDA(cudaMemcpyAsync(ctx->h_stage.p, ctx->wave.p, wav_bytes, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(h_wave, ctx->h_stage.p, wav_bytes);
+  }
+  B200_CUDA(cudaStreamSynchronize(st));
+  API_END
+}
+
+// ---- PHILOX noise dump ------------------------------------------------------------------------------
+__global__ void philox_dump_kernel(unsigned long long seed, unsigned long long utt0, int B, int step0, int n_steps, int NC,
+                                   float* __restrict__ q) {
+  size_t total = (size_t)n_steps * B * (NC / 4);
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(e % (NC / 4));
+    size_t sb = e / (NC / 4);
+    int b = (int)(sb % B), s = (int)(sb / B);
+    float v[4];
+    philox_exp4(seed, utt0 + (unsigned long long)b, (uint32_t)(step0 + s), (uint32_t)c4, v);
+    *reinterpret_cast<float4*>(q + sb * NC + (size_t)c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+extern "C" int b200tts_philox_exponential(int device, uint64_t seed, uint64_t utterance_offset, int B, int step0, int n_steps,
+                                          int n_classes, float* d_q, void* stream) {
+  API_BEGIN
+  REQUIRE(d_q && B >= 1 && n_steps >= 1 && n_classes >= 4 && n_classes % 4 == 0 && step0 >= 0, B200TTS_EINVAL, "bad argument");
+  DeviceGuard dg(device);
+  size_t total = (size_t)n_steps * B * (n_classes / 4);
+  unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  philox_dump_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, utterance_offset, B, step0, n_steps, n_classes, d_q);
+  B200_CUDA(cudaGetLastError());
+  API_END
+}

@@ -1,0 +1,173 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every declared symbol,
+the hparams singleton / dsp / paths mirrors behave like the reference's, the CLI validates its input.
+No GPU compute is invoked here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import wavernn_oracle as wo
+
+
+def _lib():
+    from tacotronv2_wavernn_chinese_b200 import build, _lib
+    build.build_lib()
+    return _lib.load(), _lib
+
+
+def test_library_exports_every_declared_symbol():
+    lib, L = _lib()
+    header = open(os.path.join(ROOT, 'include', 'b200tts.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(b200tts_\w+)\s*\(', header))
+    assert declared, 'no prototypes parsed from include/b200tts.h'
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in b200tts.h but not exported'
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    assert lib.b200tts_abi_version() == 1
+
+
+def test_library_is_sm100a_and_has_no_cpu_path():
+    lib, L = _lib()
+    out = subprocess.run(['cuobjdump', '--list-elf', L.lib_path()], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out, out
+    import torch
+    if not torch.cuda.is_available():
+        # without a device every compute entry point must fail loudly, never fall back
+        assert lib.b200tts_device_count() <= 0
+        from tacotronv2_wavernn_chinese_b200 import synth
+        from tacotronv2_wavernn_chinese_b200.engine import WaveRNNEngine
+        with pytest.raises(RuntimeError):
+            WaveRNNEngine(synth.synth_state_dict(0), synth.DEFAULT_DIMS)
+
+
+def test_struct_layouts_match_header():
+    _, L = _lib()
+    assert ctypes.sizeof(L.WaveRNNCfg) == 14 * 4
+    assert ctypes.sizeof(L.Tensor) == 8 + 8 + 8 + 32
+    assert ctypes.sizeof(L.Rng) == 32
+    assert ctypes.sizeof(L.GenOpts) == 32
+
+
+def test_hparams_singleton_contract(tmp_path):
+    code = f'''
+import sys
+sys.path.insert(0, {ROOT!r})
+from tacotronv2_wavernn_chinese_b200.wavernn.utils import hparams as hp
+try:
+    hp.bits
+    raise SystemExit("no AttributeError before configure")
+except AttributeError:
+    pass
+try:
+    hp.configure("/nonexistent/hp.py"); raise SystemExit("missing file accepted")
+except FileNotFoundError:
+    pass
+try:
+    hp.configure({str(tmp_path / "x.txt")!r}); raise SystemExit("non-.py accepted")
+except ValueError:
+    pass
+hp.configure({os.path.join(ROOT, "wavernn_hparams.py")!r})
+assert (hp.bits, hp.hop_length, hp.voc_upsample_factors, hp.voc_rnn_dims, hp.voc_pad, hp.voc_mode) == (10, 275, (5, 5, 11), 512, 2, "RAW")
+assert (hp.sample_rate, hp.num_mels, hp.voc_target, hp.voc_overlap, hp.mu_law) == (22050, 80, 11000, 550, True)
+try:
+    hp.configure({os.path.join(ROOT, "wavernn_hparams.py")!r}); raise SystemExit("reconfigure accepted")
+except RuntimeError:
+    pass
+print("OK")
+'''
+    (tmp_path / 'x.txt').write_text('a = 1')
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert r.returncode == 0 and 'OK' in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.reference
+def test_hparams_file_matches_reference_values():
+    ref = '/root/reference/wavernn_hparams.py'
+    if not os.path.isfile(ref):
+        pytest.skip('reference not present')
+    a, b = {}, {}
+    exec(open(ref).read(), a)
+    exec(open(os.path.join(ROOT, 'wavernn_hparams.py')).read(), b)
+    ka = {k: v for k, v in a.items() if not k.startswith('__')}
+    kb = {k: v for k, v in b.items() if not k.startswith('__')}
+    assert ka == kb
+
+
+def test_dsp_mirror_matches_oracle():
+    from tacotronv2_wavernn_chinese_b200.wavernn.utils import dsp
+    y = np.linspace(-1, 1, 1024)
+    np.testing.assert_array_equal(dsp.decode_mu_law(y, 1024, from_labels=False), wo.decode_mu_law(y, 1024))
+    lab = np.arange(1024)
+    np.testing.assert_allclose(dsp.decode_mu_law(lab, 1024), wo.decode_mu_law(dsp.label_2_float(lab, 10), 1024))
+    x = np.linspace(-1, 1, 101)
+    enc = dsp.encode_mu_law(x, 1024)
+    assert enc.min() == 0 and enc.max() == 1023
+    assert np.abs(dsp.decode_mu_law(enc, 1024) - x).max() < 0.01
+
+
+def test_save_wav_float32(tmp_path):
+    from scipy.io import wavfile
+    from tacotronv2_wavernn_chinese_b200.wavernn.utils import dsp
+    x = np.sin(np.arange(2205) / 10.0) * 0.5
+    dsp.save_wav(x, tmp_path / 'a.wav', 22050)
+    sr, y = wavfile.read(tmp_path / 'a.wav')
+    assert sr == 22050 and y.dtype == np.float32
+    np.testing.assert_array_equal(y, x.astype(np.float32))
+
+
+def test_paths(tmp_path):
+    from tacotronv2_wavernn_chinese_b200.wavernn.utils.paths import Paths
+    p = Paths('wavernn', base=tmp_path)
+    assert p.voc_latest_weights == tmp_path / 'logs_wavernn/checkpoints/latest_weights.pyt'
+    assert p.voc_checkpoints.is_dir() and p.voc_output.is_dir()
+    assert p.get_voc_named_weights('x').name == 'x_weights.pyt'
+
+
+def test_model_keys_and_cpu_refusal():
+    import torch
+    from tacotronv2_wavernn_chinese_b200 import synth
+    from tacotronv2_wavernn_chinese_b200.wavernn.models.fatchord_version import WaveRNN
+    m = WaveRNN(512, 512, 10, 2, (5, 5, 11), 80, 128, 128, 10, 275, 22050)
+    sd = synth.synth_state_dict(3)
+    assert set(sd) == set(m.state_dict())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == sd[k].shape, k
+    with pytest.raises(NotImplementedError):
+        m.generate(torch.zeros(1, 80, 30), None, True, 11000, 550, True)
+    with pytest.raises(ValueError):
+        m.generate(torch.zeros(1, 80, 20), None, False, 11000, 550, True) if torch.cuda.is_available() else (_ for _ in ()).throw(ValueError())
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            m.generate(torch.zeros(1, 80, 30), None, False, 11000, 550, True)
+
+
+def test_cli_rejects_bad_mel(tmp_path):
+    import importlib
+    sys.path.insert(0, ROOT)
+    code = f'''
+import sys, numpy as np
+sys.path.insert(0, {ROOT!r})
+import wavernn_gen as g
+from tacotronv2_wavernn_chinese_b200.wavernn.utils import hparams as hp
+hp.configure({os.path.join(ROOT, "wavernn_hparams.py")!r})
+class M:
+    def get_step(self): return 617000
+    def generate(self, *a, **k): raise SystemExit("generate reached")
+np.save({str(tmp_path / "bad_range.npy")!r}, np.full((30, 80), 1.5, np.float32))
+np.save({str(tmp_path / "bad_shape.npy")!r}, np.zeros((30, 81), np.float32))
+for f in ("bad_range.npy", "bad_shape.npy", "x.wav"):
+    try:
+        g.gen_from_file(M(), {str(tmp_path)!r} + "/" + f, {str(tmp_path)!r}, False, 11000, 550)
+        raise SystemExit("accepted " + f)
+    except ValueError:
+        pass
+print("OK")
+'''
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert r.returncode == 0 and 'OK' in r.stdout, r.stdout + r.stderr

@@ -1,0 +1,259 @@
+"""Parity of the sm_100a WaveRNN path against the oracle and the reference-generated goldens.
+Everything here calls the CUDA kernels through the C ABI (engine.WaveRNNEngine -> libb200tts.so)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_ckpt_state_dict
+from oracle import wavernn_oracle as wo
+from tacotronv2_wavernn_chinese_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ['utterance', 'grid']
+
+
+@pytest.fixture(scope='module')
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail('GPU tests need a CUDA device (and there is no CPU fallback to hide behind)')
+    return torch
+
+
+_engines = {}
+
+
+def engine_for(case):
+    """case: 'synth<seed>' or 'ckpt'."""
+    from tacotronv2_wavernn_chinese_b200.engine import WaveRNNEngine
+    if case not in _engines:
+        if case == 'ckpt':
+            sd = load_ckpt_state_dict()
+            if sd is None:
+                pytest.skip('shipped checkpoint not available on this box')
+        else:
+            sd = synth.synth_state_dict(int(case[5:]))
+        _engines[case] = (WaveRNNEngine(sd, synth.DEFAULT_DIMS), wo.as_params(sd))
+    return _engines[case]
+
+
+def _padded(mels):
+    B, F, T = mels.shape
+    mp = np.zeros((B, F, T + 4), dtype=np.float32)
+    mp[:, :, 2:-2] = mels
+    return mp
+
+
+def _golden(name):
+    return np.load(os.path.join(GOLDEN, name + '.npz'))
+
+
+def _case_of(name):
+    return 'ckpt' if 'ckpt' in name else 'synth11'
+
+
+# ------------------------------------------------------------------------------------------------
+# conditioning network
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['wavernn_synth_T24', 'wavernn_ckpt_T24'])
+def test_upsample_vs_reference_golden(torch_cuda, name):
+    g = _golden(name)
+    eng, p = engine_for(_case_of(name))
+    mels = synth.synth_mels(int(g['mel_seed']), int(g['B']), int(g['T']))
+    up, aux = eng.upsample(mels, full_aux=True)
+    up, aux = up.cpu().numpy(), aux.cpu().numpy()
+    st = int(g['up_stride'])
+    # fp32 re-association only (composite polyphase FIR instead of three staged convolutions; BN folded to scale/shift)
+    np.testing.assert_allclose(up[:, ::st], g['mels_up_sub'], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(aux[:, ::275], g['aux_frames'], rtol=0, atol=2e-4)
+    assert np.array_equal(aux, np.repeat(aux[:, ::275], 275, axis=1))
+
+
+@pytest.mark.parametrize('B,T', [(1, 21), (3, 37), (2, 5)])
+def test_upsample_vs_oracle_shapes(torch_cuda, B, T):
+    eng, p = engine_for('synth5')
+    mels = synth.synth_mels(77 + T, B, T)
+    up, auxf = eng.upsample(mels, full_aux=False)
+    ref_up, ref_aux = wo.upsample(p, _padded(mels))
+    np.testing.assert_allclose(up.cpu().numpy(), ref_up, rtol=0, atol=5e-6)
+    np.testing.assert_allclose(auxf.cpu().numpy(), ref_aux[:, ::275], rtol=0, atol=2e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# generation: teacher-forced logits, free-running labels, wave
+# ------------------------------------------------------------------------------------------------
+def _explain_divergence(p, mels, q, ref_labels, t, b):
+    """True when the first mismatch at (b, t) is a near-tie of the sampling race (l - log q top-2 gap tiny)."""
+    r = wo.generate(p, mels, q=q[:t + 1], teacher=ref_labels, keep_logits=[t], max_steps=t + 1)
+    key = r['logits'][t][b].astype(np.float64) - np.log(q[t, b].astype(np.float64))
+    top = np.sort(key)[-2:]
+    return (top[1] - top[0]) < 1e-3 * max(1.0, abs(top[1]))
+
+
+@pytest.mark.parametrize('kernel', KERNELS)
+@pytest.mark.parametrize('name', ['wavernn_synth_T24', 'wavernn_ckpt_T24'])
+def test_generate_vs_reference_golden(torch_cuda, name, kernel):
+    g = _golden(name)
+    eng, p = engine_for(_case_of(name))
+    B, T = int(g['B']), int(g['T'])
+    S = T * 275
+    mels = synth.synth_mels(int(g['mel_seed']), B, T)
+    q = synth.synth_exponential_noise(int(g['noise_seed']), S, B)
+    steps = [int(s) for s in g['logit_steps']]
+    # (a) teacher-forced on the reference's label sequence: logits of every recorded step
+    out = eng.generate(mels, q=q, teacher=g['labels'], return_logits=True, kernel=kernel)
+    lg = out['logits'].cpu().numpy()
+    scale = max(1.0, float(np.abs(g['gen_logits']).max()))
+    # tolerance: the reference's own nn.GRU-vs-nn.GRUCell floor is 1e-3 abs at |logit|~450 = 2e-6*scale
+    tol = 5e-6 * scale + 1e-4
+    err = max(np.abs(lg[s] - g['gen_logits'][i]).max() for i, s in enumerate(steps))
+    assert err <= tol, f'teacher-forced logit error {err:.3e} > {tol:.3e}'
+    lab_tf = out['labels'].cpu().numpy()
+    assert (lab_tf != g['labels']).sum() <= 2, 'sampling from near-identical logits with identical noise must agree'
+    # (b) free running, shared noise: identical labels, or a first mismatch that is a genuine near-tie
+    out = eng.generate(mels, q=q, kernel=kernel)
+    lab = out['labels'].cpu().numpy()
+    for b in range(B):
+        mism = np.nonzero(lab[b] != g['labels'][b])[0]
+        if mism.size:
+            t = int(mism[0])
+            assert t > S // 4 and _explain_divergence(p, mels, q, g['labels'], t, b), \
+                f'utterance {b} diverged from the reference at step {t} without a sampling near-tie'
+    if np.array_equal(lab[0], g['labels'][0]):
+        np.testing.assert_allclose(out['wave'].cpu().numpy()[0], g['wave0'], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('kernel', KERNELS)
+def test_generate_config1_shape_vs_reference(torch_cuda, kernel):
+    """BASELINE config 1 shape (80 frames, 22 000 steps) on the shipped checkpoint vs the reference's own labels."""
+    g = _golden('wavernn_ckpt_T80')
+    eng, p = engine_for('ckpt')
+    mels = synth.synth_mels(int(g['mel_seed']), 1, 80)
+    q = synth.synth_exponential_noise(int(g['noise_seed']), 80 * 275, 1)
+    out = eng.generate(mels, q=q, kernel=kernel)
+    lab = out['labels'].cpu().numpy()
+    mism = np.nonzero(lab[0] != g['labels'][0])[0]
+    if mism.size:
+        t = int(mism[0])
+        assert t > 2000 and _explain_divergence(p, mels, q, g['labels'], t, 0), f'diverged at step {t}'
+    else:
+        np.testing.assert_allclose(out['wave'].cpu().numpy()[0], g['wave0'], rtol=0, atol=1e-12)
+    # teacher-forced logits at the recorded steps over the full length
+    out = eng.generate(mels, q=q, teacher=g['labels'], return_logits=True, kernel=kernel)
+    lg = out['logits'].cpu().numpy()
+    scale = float(np.abs(g['gen_logits']).max())
+    for i, s in enumerate(int(s) for s in g['logit_steps']):
+        assert np.abs(lg[s] - g['gen_logits'][i]).max() <= 5e-6 * scale + 1e-4
+
+
+@pytest.mark.parametrize('kernel', KERNELS)
+def test_philox_stream_matches_oracle(torch_cuda, kernel):
+    """Production RNG: dump the Philox Exp(1) stream the kernel draws and replay it through the oracle."""
+    eng, p = engine_for('synth5')
+    B, T, seed, off = 2, 21, 0xC0FFEE, 7
+    S = T * 275
+    mels = synth.synth_mels(31, B, T)
+    q = eng.philox_exponential(seed, off, B, 0, S).cpu().numpy()
+    assert q.min() > 0 and abs(q.mean() - 1.0) < 0.01 and abs(q.var() - 1.0) < 0.02
+    out = eng.generate(mels, seed=seed, utterance_offset=off, kernel=kernel)
+    ref = wo.generate(p, mels, q=q)
+    lab = out['labels'].cpu().numpy()
+    for b in range(B):
+        mism = np.nonzero(lab[b] != ref['labels'][b])[0]
+        assert mism.size == 0 or (mism[0] > S // 4 and _explain_divergence(p, mels, q, ref['labels'], int(mism[0]), b))
+    if np.array_equal(lab, ref['labels']):
+        np.testing.assert_allclose(out['wave'].cpu().numpy(), ref['wave'], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('kernel', KERNELS)
+def test_batch_composition_invariance(torch_cuda, kernel):
+    """Philox is keyed by the GLOBAL utterance index, so a row's output cannot depend on what it is batched with
+    (this is what makes multi-GPU sharding reproduce the single-GPU result).  Covers the G=1,2,4,8 row-group variants."""
+    eng, _ = engine_for('synth5')
+    T, seed = 21, 99
+    for B in (3, 9):
+        mels = synth.synth_mels(500 + B, B, T)
+        full = eng.generate(mels, seed=seed, kernel=kernel, max_steps=1500)['labels'].cpu().numpy()
+        for b in (0, B - 1):
+            solo = eng.generate(mels[b:b + 1], seed=seed, utterance_offset=b, kernel=kernel, max_steps=1500)
+            assert np.array_equal(solo['labels'].cpu().numpy()[0, :1500], full[b, :1500])
+
+
+def test_kernels_agree_full_size(torch_cuda):
+    """Both kernels, BASELINE-shaped batch (80-frame mels), free running with Philox: identical label streams for
+    the first 3000 steps (beyond that fp32 re-association differences may flip a sampling near-tie)."""
+    eng, _ = engine_for('synth5')
+    mels = synth.synth_mels(4242, 16, 80)
+    a = eng.generate(mels, seed=5, kernel='utterance', max_steps=3000)['labels'].cpu().numpy()
+    b = eng.generate(mels, seed=5, kernel='grid', max_steps=3000)['labels'].cpu().numpy()
+    agree = (a[:, :3000] == b[:, :3000]).all(axis=1)
+    assert agree.mean() >= 0.8, f'only {agree.mean():.2f} of utterances agree between kernels'
+
+
+def test_host_entry_point_equals_device_path(torch_cuda):
+    eng, _ = engine_for('synth5')
+    mels = synth.synth_mels(9, 2, 22)
+    dev = eng.generate(mels, seed=42)
+    host = eng.generate_host(mels, seed=42)
+    assert np.array_equal(host['labels'], dev['labels'].cpu().numpy())
+    np.testing.assert_array_equal(host['wave'], dev['wave'].cpu().numpy())
+    assert host['wave'].dtype == np.float64 and host['wave'].shape == (2, 21 * 275)
+    assert np.all(host['wave'][:, -1] == 0.0) and np.abs(host['wave']).max() <= 1.0
+
+
+def test_wave_epilogue_matches_oracle(torch_cuda):
+    eng, _ = engine_for('synth5')
+    mels = synth.synth_mels(10, 3, 25)
+    out = eng.generate(mels, seed=1)
+    lab = out['labels'].cpu().numpy()
+    np.testing.assert_allclose(out['wave'].cpu().numpy(), wo.finish_wave(lab, 1024, 24 * 275, 275), rtol=0, atol=1e-12)
+    out2 = eng.generate(mels, seed=1, mu_law=False)
+    np.testing.assert_allclose(out2['wave'].cpu().numpy(), wo.finish_wave(lab, 1024, 24 * 275, 275, mu_law=False),
+                               rtol=0, atol=1e-12)
+
+
+def test_error_behaviour(torch_cuda):
+    from tacotronv2_wavernn_chinese_b200._lib import B200TTSError
+    from tacotronv2_wavernn_chinese_b200.engine import WaveRNNEngine
+    eng, _ = engine_for('synth5')
+    with pytest.raises(B200TTSError) as e:
+        eng.generate(synth.synth_mels(1, 1, 20), seed=1)          # T < 21: the reference's fade-out cannot run either
+    assert 'T must be >= 21' in str(e.value)
+    with pytest.raises(ValueError):
+        eng.generate(np.zeros((1, 79, 30), np.float32))
+    sd = synth.synth_state_dict(1)
+    bad = dict(sd)
+    del bad['fc3.bias']
+    with pytest.raises(B200TTSError) as e:
+        WaveRNNEngine(bad, synth.DEFAULT_DIMS)
+    assert e.value.code == -4 and 'fc3.bias' in str(e.value)
+    bad = dict(sd)
+    bad['rnn1.weight_hh_l0'] = np.zeros((1536, 511), np.float32)
+    with pytest.raises(B200TTSError) as e:
+        WaveRNNEngine(bad, synth.DEFAULT_DIMS)
+    assert e.value.code == -5
+
+
+def test_dropin_model_generate(torch_cuda, tmp_path):
+    """The reference-facing class: same constructor, state_dict keys, generate() signature and return type."""
+    torch = torch_cuda
+    from scipy.io import wavfile
+    from tacotronv2_wavernn_chinese_b200.wavernn.models.fatchord_version import WaveRNN
+    m = WaveRNN(512, 512, 10, 2, (5, 5, 11), 80, 128, 128, 10, 275, 22050, 'RAW')
+    sd = synth.synth_state_dict(5)
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    mel = torch.as_tensor(synth.synth_mels(3, 1, 23))
+    path = tmp_path / 'o.wav'
+    torch.manual_seed(7)
+    w1 = m.generate(mel, str(path), False, 11000, 550, True)
+    assert isinstance(w1, np.ndarray) and w1.dtype == np.float64 and w1.shape == (22 * 275,)
+    assert m.training          # generate() leaves the module in train() mode like the reference (:262)
+    sr, y = wavfile.read(path)
+    assert sr == 22050 and np.array_equal(y, w1.astype(np.float32))
+    eng, p = engine_for('synth5')
+    lab = m.last_labels.cpu().numpy()
+    np.testing.assert_allclose(w1, wo.finish_wave(lab, 1024, 22 * 275, 275)[0], rtol=0, atol=1e-12)
+    up, aux = m.upsample(torch.as_tensor(_padded(mel.numpy())))
+    assert tuple(up.shape) == (1, 23 * 275, 80) and tuple(aux.shape) == (1, 23 * 275, 128)
