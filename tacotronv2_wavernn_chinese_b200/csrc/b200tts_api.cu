@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "wavernn_upsample.cuh"
 #include "wavernn_utt.cuh"
+#include "wavernn_grid.cuh"
 
 using namespace b200tts;
 
@@ -147,6 +148,9 @@ struct b200tts_wavernn {
   StepWeights sw{};
   ResnetParams rp{};
   const float* d_fir = nullptr;   // [hop][NT]
+  GridModel gm{};                 // per-CTA weight blobs of the grid kernel
+  DeviceBuf grid_blob, mels_T, aux_T, grid_sync;
+  int coop = 0;
   // scratch
   DeviceBuf mels_up, aux_frames, labels, mel_in, wave, grid_scratch;
   HostPinned h_stage;
@@ -343,6 +347,60 @@ extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b
   rp.feat = FEAT; rp.k = K; rp.C = C; rp.O = O; rp.blocks = c.res_blocks; rp.pad = c.pad;
   ctx->d_fir = base + o_fir;
 
+  // ---- weight-stationary per-CTA blobs for the grid kernel (wavernn_grid.cuh) ----
+  {
+    GridModel& g = ctx->gm;
+    g.R = R; g.F = F; g.AUX = AUX; g.FEAT = FEAT; g.NC = NC;
+    g.ldC = FEAT + AUX; g.ldX = R + AUX; g.ldF = F + AUX;
+    g.ncta = R / kUPC;
+    g.ok = (R == F) && (R % kUPC == 0) && (NC == g.ncta * kCPC) && (FEAT % 4 == 0) && (g.ncta <= ctx->sm_count);
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += (n + 3) & ~3; return o; };
+    g.oI_w = take(kUPC * g.ldC); g.oI_x = take(kUPC); g.oI_b = take(kUPC);
+    g.oih1 = take(3 * kUPC * R); g.ohh1 = take(3 * kUPC * R); g.oih2 = take(3 * kUPC * g.ldX); g.ohh2 = take(3 * kUPC * R);
+    g.ofc1 = take(kUPC * g.ldX); g.ofc2 = take(kUPC * g.ldF); g.ofc3 = take(kCPC * F);
+    g.obih1 = take(3 * kUPC); g.obhh1 = take(3 * kUPC); g.obih2 = take(3 * kUPC); g.obhh2 = take(3 * kUPC);
+    g.obfc1 = take(kUPC); g.obfc2 = take(kUPC); g.obfc3 = take(kCPC);
+    g.blob = off;
+    size_t smem_need = ((size_t)g.blob + 8 * 12 * 32 * 4) * sizeof(float) + 2048;
+    if (smem_need > 227 * 1024) g.ok = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, device));
+    if (!ctx->coop) g.ok = 0;
+    if (g.ok) {
+      std::vector<float> hb((size_t)g.ncta * g.blob, 0.f);
+      const float* P = pk.h.data();
+      for (int cta = 0; cta < g.ncta; ++cta) {
+        float* b = &hb[(size_t)cta * g.blob];
+        for (int j = 0; j < kUPC; ++j) {
+          const int row = cta * kUPC + j;
+          const float* src = P + oI + (size_t)row * ldI;          // [x | feat | aux] padded
+          b[g.oI_x + j] = src[0];
+          std::memcpy(b + g.oI_w + (size_t)j * g.ldC, src + 1, sizeof(float) * g.ldC);
+          b[g.oI_b + j] = P[oIb + row];
+          std::memcpy(b + g.ofc1 + (size_t)j * g.ldX, P + o_fc1 + (size_t)row * g.ldX, sizeof(float) * g.ldX);
+          std::memcpy(b + g.ofc2 + (size_t)j * g.ldF, P + o_fc2 + (size_t)row * g.ldF, sizeof(float) * g.ldF);
+          b[g.obfc1 + j] = P[o_fc1b + row];
+          b[g.obfc2 + j] = P[o_fc2b + row];
+          for (int gate = 0; gate < 3; ++gate) {
+            const int srow = gate * R + row, drow = gate * kUPC + j;
+            std::memcpy(b + g.oih1 + (size_t)drow * R, P + o_ih1 + (size_t)srow * R, sizeof(float) * R);
+            std::memcpy(b + g.ohh1 + (size_t)drow * R, P + o_hh1 + (size_t)srow * R, sizeof(float) * R);
+            std::memcpy(b + g.oih2 + (size_t)drow * g.ldX, P + o_ih2 + (size_t)srow * g.ldX, sizeof(float) * g.ldX);
+            std::memcpy(b + g.ohh2 + (size_t)drow * R, P + o_hh2 + (size_t)srow * R, sizeof(float) * R);
+            b[g.obih1 + drow] = P[o_bih1 + srow]; b[g.obhh1 + drow] = P[o_bhh1 + srow];
+            b[g.obih2 + drow] = P[o_bih2 + srow]; b[g.obhh2 + drow] = P[o_bhh2 + srow];
+          }
+        }
+        for (int r = 0; r < kCPC; ++r) {
+          const int row = cta * kCPC + r;
+          std::memcpy(b + g.ofc3 + (size_t)r * F, P + o_fc3 + (size_t)row * F, sizeof(float) * F);
+          b[g.obfc3 + r] = P[o_fc3b + row];
+        }
+      }
+      ctx->grid_blob.ensure(hb.size() * sizeof(float));
+      B200_CUDA(cudaMemcpy(ctx->grid_blob.p, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+  }
   B200_CUDA(cudaEventCreate(&ctx->ev0));
   B200_CUDA(cudaEventCreate(&ctx->ev1));
   cleanup.c = nullptr;
@@ -362,6 +420,10 @@ extern "C" void b200tts_wavernn_destroy(b200tts_wavernn* ctx) {
   ctx->mel_in.release();
   ctx->wave.release();
   ctx->grid_scratch.release();
+  ctx->grid_blob.release();
+  ctx->mels_T.release();
+  ctx->aux_T.release();
+  ctx->grid_sync.release();
   ctx->h_stage.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -448,6 +510,87 @@ static void launch_utt(b200tts_wavernn* ctx, const GenArgs& a, cudaStream_t st) 
   ctx->launches++;
 }
 
+template <int U, int UW>
+static void launch_grid_t(b200tts_wavernn* ctx, GridArgs& a, cudaStream_t st) {
+  const GridModel& g = ctx->gm;
+  size_t part = MapTraits<U, UW>::kWide ? (size_t)(8 / UW) * 12 * MapTraits<U, UW>::BT : (size_t)2 * 12 * UW;
+  size_t smem = ((size_t)g.blob + part) * sizeof(float);
+  auto kern = wavernn_grid_kernel<U, UW>;
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGridThreads, smem));
+  REQUIRE(per_sm * ctx->sm_count >= g.ncta, B200TTS_EINVAL, "grid kernel cannot be made co-resident on this device");
+  GridModel gm = g;
+  void* args[] = {(void*)&gm, (void*)&a};
+  B200_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(g.ncta), dim3(kGridThreads), args, smem, st));
+  ctx->launches++;
+}
+
+// returns the padded batch the grid kernel will use for B utterances
+static int grid_padded_batch(int B, int* U, int* UW) {
+  if (B <= 4) { *U = 0; *UW = 4; return 4; }
+  if (B <= 8) { *U = 0; *UW = 8; return 8; }
+  if (B <= 32) { *U = 1; *UW = 1; return 32; }
+  if (B <= 64) { *U = 2; *UW = 1; return 64; }
+  if (B <= 128) { *U = 4; *UW = 1; return 128; }
+  int p256 = (B + 255) / 256 * 256, p128 = (B + 127) / 128 * 128;
+  if (p128 < p256) { *U = 4; *UW = 1; return p128; }
+  *U = 4; *UW = 2; return p256;
+}
+
+static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cudaStream_t st) {
+  const b200tts_wavernn_cfg& c = ctx->cfg;
+  const GridModel& g = ctx->gm;
+  REQUIRE(g.ok, B200TTS_EINVAL, "this model/device cannot run the grid kernel (use B200TTS_KERNEL_UTTERANCE)");
+  int U = 0, UW = 0;
+  const int B = ua.B, T = ua.T, S = ua.S, O = c.res_out_dims;
+  const int Bp = grid_padded_batch(B, &U, &UW);
+  // conditioning in K-major layout
+  ctx->mels_T.ensure((size_t)S * c.feat_dims * Bp * sizeof(float));
+  ctx->aux_T.ensure((size_t)T * O * Bp * sizeof(float));
+  {
+    size_t n = (size_t)S * c.feat_dims * Bp;
+    unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 32);
+    mel_fir_T_kernel<<<grid, 256, 0, st>>>(d_mel, ctx->d_fir, B, Bp, T, c.feat_dims, c.hop_length, c.pad, ctx->NT,
+                                           ctx->mels_T.as<float>());
+    B200_CUDA(cudaGetLastError());
+    n = (size_t)T * O * Bp;
+    grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 32);
+    aux_T_kernel<<<grid, 256, 0, st>>>(ua.aux_frames, B, Bp, T, O, ctx->aux_T.as<float>());
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+  }
+  // activations + sync words, zero-initialised (h1 = h2 = 0, fatchord_version.py:194-195)
+  const size_t RB = (size_t)g.R * Bp;
+  const size_t act_floats = 9 * RB;
+  const size_t sync_bytes = 2 * (size_t)Bp * sizeof(unsigned long long) + 256;
+  ctx->grid_scratch.ensure(act_floats * sizeof(float));
+  ctx->grid_sync.ensure(sync_bytes);
+  B200_CUDA(cudaMemsetAsync(ctx->grid_scratch.p, 0, act_floats * sizeof(float), st));
+  B200_CUDA(cudaMemsetAsync(ctx->grid_sync.p, 0, sync_bytes, st));
+  float* base = ctx->grid_scratch.as<float>();
+  GridArgs a{};
+  a.wblob = ctx->grid_blob.as<float>();
+  a.Iout = base; a.h1 = base + RB; a.h2 = base + 3 * RB; a.x1 = base + 5 * RB; a.x2 = base + 6 * RB;
+  a.f1 = base + 7 * RB; a.f2 = base + 8 * RB;
+  a.best = ctx->grid_sync.as<unsigned long long>();
+  a.barrier = reinterpret_cast<unsigned int*>(ctx->grid_sync.as<char>() + 2 * (size_t)Bp * sizeof(unsigned long long));
+  a.error = reinterpret_cast<int*>(a.barrier + 16);
+  a.mels_T = ctx->mels_T.as<float>();
+  a.aux_T = ctx->aux_T.as<float>();
+  a.B = B; a.Bp = Bp; a.S = S; a.T = T; a.hop = ua.hop; a.steps = ua.steps;
+  a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.q = ua.q;
+  a.teacher = ua.teacher; a.logits_out = ua.logits_out; a.labels = ua.labels;
+  B200_CUDA(cudaEventRecord(ctx->ev0, st));
+  if (U == 0 && UW == 4) launch_grid_t<0, 4>(ctx, a, st);
+  else if (U == 0) launch_grid_t<0, 8>(ctx, a, st);
+  else if (U == 1) launch_grid_t<1, 1>(ctx, a, st);
+  else if (U == 2) launch_grid_t<2, 1>(ctx, a, st);
+  else if (UW == 1) launch_grid_t<4, 1>(ctx, a, st);
+  else launch_grid_t<4, 2>(ctx, a, st);
+  B200_CUDA(cudaEventRecord(ctx->ev1, st));
+}
+
 static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
                          const b200tts_gen_opts* opts, int16_t* d_labels, double* d_wave, cudaStream_t st) {
   const b200tts_wavernn_cfg& c = ctx->cfg;
@@ -468,14 +611,21 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
     REQUIRE(wave_len >= fade_len, B200TTS_EINVAL,
             "T must be >= 21 frames: the reference's 20-hop fade-out (fatchord_version.py:256-258) fails below that");
   }
-  ctx->mels_up.ensure((size_t)B * S * c.feat_dims * sizeof(float));
+  int kernel = o.kernel;
+  if (kernel == B200TTS_KERNEL_AUTO) kernel = ctx->gm.ok ? B200TTS_KERNEL_GRID : B200TTS_KERNEL_UTTERANCE;
+  REQUIRE(kernel == B200TTS_KERNEL_UTTERANCE || kernel == B200TTS_KERNEL_GRID, B200TTS_EINVAL, "unknown kernel selector");
   ctx->aux_frames.ensure((size_t)B * T * O * sizeof(float));
   int16_t* labels = d_labels;
   if (!labels) {
     ctx->labels.ensure((size_t)B * S * sizeof(int16_t));
     labels = ctx->labels.as<int16_t>();
   }
-  run_upsample(ctx, d_mel, B, T, ctx->mels_up.as<float>(), ctx->aux_frames.as<float>(), nullptr, st);
+  float* mels_up = nullptr;
+  if (kernel == B200TTS_KERNEL_UTTERANCE) {
+    ctx->mels_up.ensure((size_t)B * S * c.feat_dims * sizeof(float));
+    mels_up = ctx->mels_up.as<float>();
+  }
+  run_upsample(ctx, d_mel, B, T, mels_up, ctx->aux_frames.as<float>(), nullptr, st);
 
   GenArgs a{};
   a.mels_up = ctx->mels_up.as<float>();
@@ -484,20 +634,18 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
   a.rng_mode = r.mode; a.seed = r.seed; a.utt_offset = r.utterance_offset; a.q = r.d_q;
   a.teacher = o.d_teacher; a.logits_out = o.d_logits; a.labels = labels;
 
-  int kernel = o.kernel;
-  if (kernel == B200TTS_KERNEL_AUTO) kernel = B200TTS_KERNEL_UTTERANCE;
-  B200_CUDA(cudaEventRecord(ctx->ev0, st));
   if (kernel == B200TTS_KERNEL_UTTERANCE) {
+    B200_CUDA(cudaEventRecord(ctx->ev0, st));
     // utterances per CTA: enough CTAs to cover the SMs first, then amortise the L2 weight stream over more rows
     int per = (B + ctx->sm_count - 1) / ctx->sm_count;
     if (per <= 1) launch_utt<1>(ctx, a, st);
     else if (per <= 2) launch_utt<2>(ctx, a, st);
     else if (per <= 4) launch_utt<4>(ctx, a, st);
     else launch_utt<8>(ctx, a, st);
+    B200_CUDA(cudaEventRecord(ctx->ev1, st));
   } else {
-    throw Error(B200TTS_EINVAL, "unknown kernel selector");
+    launch_grid(ctx, d_mel, a, st);
   }
-  B200_CUDA(cudaEventRecord(ctx->ev1, st));
   ctx->ev_valid = true;
   if (d_wave) {
     dim3 grid((wave_len + 255) / 256, B);
