@@ -12,7 +12,6 @@
  *   b200tts_wavernn_generate   <- WaveRNN.generate (unbatched branch)   wavernn/models/fatchord_version.py:169-264
  *                                 incl. decode_mu_law                   wavernn/utils/dsp.py:98-103
  *   b200tts_wavernn_generate_host  same, HOST buffers in/out (what wavernn_gen.py:41 sees end to end)
- *   b200tts_wavernn_fold / _xfade  <- fold_with_overlap / xfade_and_unfold  fatchord_version.py:293-405 (opt-in --batched)
  *
  * Conventions
  *   - plain C types only; no torch / CUDA types in any signature (`stream` is a cudaStream_t passed as void*).
@@ -134,6 +133,10 @@ int64_t b200tts_wavernn_launch_count(const b200tts_wavernn* ctx);
 /* Milliseconds (CUDA events on the launch stream) spent in the per-sample generation kernel by the most recent
  * generate call; blocks until that kernel has finished.  Negative on error. */
 double b200tts_wavernn_last_kernel_ms(b200tts_wavernn* ctx);
+
+/* Debug aid: mean SM cycles per CTA spent in {compute, barrier} of each of the 6 phases of the last grid-kernel
+ * launch; only recorded when the environment variable B200TTS_GRID_PROF is set while generating. */
+int b200tts_wavernn_debug_phase_cycles(b200tts_wavernn* ctx, double* out12);
 
 #ifdef __cplusplus
 }

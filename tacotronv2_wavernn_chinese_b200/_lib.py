@@ -62,6 +62,7 @@ SIGNATURES = {
                                              C.c_void_p, C.c_void_p]),
     'b200tts_wavernn_launch_count': (C.c_int64, [C.c_void_p]),
     'b200tts_wavernn_last_kernel_ms': (C.c_double, [C.c_void_p]),
+    'b200tts_wavernn_debug_phase_cycles': (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }
 
 _lib = None

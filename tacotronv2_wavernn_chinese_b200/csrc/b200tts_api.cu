@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -149,7 +150,8 @@ struct b200tts_wavernn {
   ResnetParams rp{};
   const float* d_fir = nullptr;   // [hop][NT]
   GridModel gm{};                 // per-CTA weight blobs of the grid kernel
-  DeviceBuf grid_blob, mels_T, aux_T, grid_sync;
+  DeviceBuf grid_blob, mels_T, aux_T, grid_sync, grid_prof;
+  int last_grid_ncta = 0;
   int coop = 0;
   // scratch
   DeviceBuf mels_up, aux_frames, labels, mel_in, wave, grid_scratch;
@@ -362,7 +364,7 @@ extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b
     g.obih1 = take(3 * kUPC); g.obhh1 = take(3 * kUPC); g.obih2 = take(3 * kUPC); g.obhh2 = take(3 * kUPC);
     g.obfc1 = take(kUPC); g.obfc2 = take(kUPC); g.obfc3 = take(kCPC);
     g.blob = off;
-    size_t smem_need = ((size_t)g.blob + 8 * 12 * 32 * 4) * sizeof(float) + 2048;
+    size_t smem_need = ((size_t)g.blob + (size_t)MapTraits<4, 2>::kScratchFloats) * sizeof(float) + 2048;
     if (smem_need > 227 * 1024) g.ok = 0;
     B200_CUDA(cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, device));
     if (!ctx->coop) g.ok = 0;
@@ -424,6 +426,7 @@ extern "C" void b200tts_wavernn_destroy(b200tts_wavernn* ctx) {
   ctx->mels_T.release();
   ctx->aux_T.release();
   ctx->grid_sync.release();
+  ctx->grid_prof.release();
   ctx->h_stage.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -513,16 +516,17 @@ static void launch_utt(b200tts_wavernn* ctx, const GenArgs& a, cudaStream_t st) 
 template <int U, int UW>
 static void launch_grid_t(b200tts_wavernn* ctx, GridArgs& a, cudaStream_t st) {
   const GridModel& g = ctx->gm;
-  size_t part = MapTraits<U, UW>::kWide ? (size_t)(8 / UW) * 12 * MapTraits<U, UW>::BT : (size_t)2 * 12 * UW;
-  size_t smem = ((size_t)g.blob + part) * sizeof(float);
+  using MT = MapTraits<U, UW>;
+  constexpr int kThreads = MT::NW * 32;
+  size_t smem = ((size_t)g.blob + (size_t)MT::kScratchFloats) * sizeof(float);
   auto kern = wavernn_grid_kernel<U, UW>;
   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGridThreads, smem));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   REQUIRE(per_sm * ctx->sm_count >= g.ncta, B200TTS_EINVAL, "grid kernel cannot be made co-resident on this device");
   GridModel gm = g;
   void* args[] = {(void*)&gm, (void*)&a};
-  B200_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(g.ncta), dim3(kGridThreads), args, smem, st));
+  B200_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(g.ncta), dim3(kThreads), args, smem, st));
   ctx->launches++;
 }
 
@@ -581,6 +585,13 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   a.B = B; a.Bp = Bp; a.S = S; a.T = T; a.hop = ua.hop; a.steps = ua.steps;
   a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.q = ua.q;
   a.teacher = ua.teacher; a.logits_out = ua.logits_out; a.labels = ua.labels;
+  a.prof = nullptr;
+  if (getenv("B200TTS_GRID_PROF")) {
+    ctx->grid_prof.ensure((size_t)g.ncta * 12 * sizeof(long long));
+    B200_CUDA(cudaMemsetAsync(ctx->grid_prof.p, 0, (size_t)g.ncta * 12 * sizeof(long long), st));
+    a.prof = ctx->grid_prof.as<long long>();
+    ctx->last_grid_ncta = g.ncta;
+  }
   B200_CUDA(cudaEventRecord(ctx->ev0, st));
   if (U == 0 && UW == 4) launch_grid_t<0, 4>(ctx, a, st);
   else if (U == 0) launch_grid_t<0, 8>(ctx, a, st);
@@ -700,6 +711,23 @@ extern "C" int b200tts_wavernn_generate_host(b200tts_wavernn* ctx, const float* 
     std::memcpy(h_wave, ctx->h_stage.p, wav_bytes);
   }
   B200_CUDA(cudaStreamSynchronize(st));
+  API_END
+}
+
+// Debug: per-phase cycle counters of the last grid-kernel launch (needs env B200TTS_GRID_PROF=1 at generate time).
+// out[12] = mean over CTAs of {P0 compute, P0 barrier, P1 compute, P1 barrier, ...} in SM cycles.
+extern "C" int b200tts_wavernn_debug_phase_cycles(b200tts_wavernn* ctx, double* out12) {
+  API_BEGIN
+  REQUIRE(ctx && out12 && ctx->grid_prof.p && ctx->last_grid_ncta > 0, B200TTS_EINVAL, "no phase profile recorded");
+  DeviceGuard dg(ctx->device);
+  std::vector<long long> h((size_t)ctx->last_grid_ncta * 12);
+  B200_CUDA(cudaDeviceSynchronize());
+  B200_CUDA(cudaMemcpy(h.data(), ctx->grid_prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 12; ++i) {
+    double s = 0;
+    for (int c = 0; c < ctx->last_grid_ncta; ++c) s += (double)h[(size_t)c * 12 + i];
+    out12[i] = s / ctx->last_grid_ncta;
+  }
   API_END
 }
 

@@ -23,8 +23,14 @@
 
 namespace b200tts {
 
-constexpr int kGridThreads = 256;
-constexpr int kGridWarps = kGridThreads / 32;
+#ifndef B200_GRID_NW_WIDE
+#define B200_GRID_NW_WIDE 8            // wide mapping: warps per CTA (measured: 12 warps spill at 168 regs and lose)
+#endif
+#ifndef B200_GRID_PF
+#define B200_GRID_PF 0                 // explicit activation prefetch distance (0 = leave it to ptxas: measured fastest)
+#endif
+constexpr int kGridWarpsWide = B200_GRID_NW_WIDE;
+constexpr int kGridWarpsNarrow = 8;
 constexpr int kUPC = 4;   // hidden units (and fc1/fc2 rows) per CTA
 constexpr int kCPC = 8;   // classes (fc3 rows) per CTA
 
@@ -62,6 +68,7 @@ struct GridArgs {
   const int16_t* teacher;      // [B][S]
   float* logits_out;           // [S][B][NC]
   int16_t* labels;             // [B][S]
+  long long* prof;             // optional [ncta][12]: cycles spent in compute / barrier of each phase (debug)
 };
 
 // ---- grid-wide barrier --------------------------------------------------------------------------------------------
@@ -134,38 +141,77 @@ struct Gemm {           // rows x (sum of segs) weight block in shared memory
 };
 
 // acc[r][u] += sum_{c4 in [lo,hi)} W[r][4*(col4+c4) .. +3] . act[4*c4 .. +3][u0 .. u0+U)
+// The activation loads come from L2 (~1 us under load) and only 3 warps share a scheduler, so they are software
+// pipelined two iterations (8 k rows) ahead in registers: three rotating buffers, loads of c4+2 issued before the
+// FMAs of c4.
+template <int U, int RT>
+__device__ __forceinline__ void wide_fma4(float (&acc)[RT][U], const float4* __restrict__ W4, int ldw4, int c4,
+                                          const float (&a)[4][U]) {
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    float4 w = W4[r * ldw4 + c4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      acc[r][u] = fmaf(w.x, a[0][u], acc[r][u]);
+      acc[r][u] = fmaf(w.y, a[1][u], acc[r][u]);
+      acc[r][u] = fmaf(w.z, a[2][u], acc[r][u]);
+      acc[r][u] = fmaf(w.w, a[3][u], acc[r][u]);
+    }
+  }
+}
+template <int U>
+__device__ __forceinline__ void wide_ld4(float (&a)[4][U], const float* __restrict__ act, size_t Bp, int c4, int hi) {
+  if (c4 < hi) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) ActLoad<U>::ld(act + (size_t)(4 * c4 + kk) * Bp, a[kk]);
+  }
+}
 template <int U, int RT>
 __device__ __forceinline__ void wide_accumulate(float (&acc)[RT][U], const float* __restrict__ W, int ldw, int col4,
                                                 const float* __restrict__ act, int Bp, int u0, int lo, int hi) {
   const float4* W4 = reinterpret_cast<const float4*>(W) + col4;
   const int ldw4 = ldw >> 2;
+  const float* ap = act + u0;
+#if B200_GRID_PF == 2
+  float a0[4][U], a1[4][U], a2[4][U];
+  wide_ld4<U>(a0, ap, Bp, lo, hi);
+  wide_ld4<U>(a1, ap, Bp, lo + 1, hi);
+  for (int c4 = lo; c4 < hi; c4 += 3) {
+    wide_ld4<U>(a2, ap, Bp, c4 + 2, hi);
+    wide_fma4<U, RT>(acc, W4, ldw4, c4, a0);
+    wide_ld4<U>(a0, ap, Bp, c4 + 3, hi);
+    if (c4 + 1 < hi) wide_fma4<U, RT>(acc, W4, ldw4, c4 + 1, a1);
+    wide_ld4<U>(a1, ap, Bp, c4 + 4, hi);
+    if (c4 + 2 < hi) wide_fma4<U, RT>(acc, W4, ldw4, c4 + 2, a2);
+  }
+#elif B200_GRID_PF == 0
 #pragma unroll 2
   for (int c4 = lo; c4 < hi; ++c4) {
     float a[4][U];
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) ActLoad<U>::ld(act + (size_t)(4 * c4 + kk) * Bp + u0, a[kk]);
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      float4 w = W4[r * ldw4 + c4];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        acc[r][u] = fmaf(w.x, a[0][u], acc[r][u]);
-        acc[r][u] = fmaf(w.y, a[1][u], acc[r][u]);
-        acc[r][u] = fmaf(w.z, a[2][u], acc[r][u]);
-        acc[r][u] = fmaf(w.w, a[3][u], acc[r][u]);
-      }
-    }
+    for (int kk = 0; kk < 4; ++kk) ActLoad<U>::ld(ap + (size_t)(4 * c4 + kk) * Bp, a[kk]);
+    wide_fma4<U, RT>(acc, W4, ldw4, c4, a);
   }
+#else
+  float a0[4][U], a1[4][U];
+  wide_ld4<U>(a0, ap, Bp, lo, hi);
+  for (int c4 = lo; c4 < hi; c4 += 2) {
+    wide_ld4<U>(a1, ap, Bp, c4 + 1, hi);
+    wide_fma4<U, RT>(acc, W4, ldw4, c4, a0);
+    wide_ld4<U>(a0, ap, Bp, c4 + 2, hi);
+    if (c4 + 1 < hi) wide_fma4<U, RT>(acc, W4, ldw4, c4 + 1, a1);
+  }
+#endif
 }
 
 // Wide mapping: NG GEMMs of RT rows each; 8 warps = NG x UW (utterance warps) x KS (k slices).
 // Partial sums land in part[((g*KS + ks)*RT + r)*BT + ul].
-template <int U, int UW, int RT, int NG>
+template <int NW, int U, int UW, int RT, int NG>
 __device__ __forceinline__ void wide_partials(float* part, const Gemm& g0, const Gemm& g1, int tile_base, int Bp, int warp,
                                               int lane) {
-  constexpr int KS = kGridWarps / (NG * UW);
+  constexpr int KS = NW / (NG * UW);
   constexpr int BT = 32 * U * UW;
-  static_assert(KS >= 1, "too many jobs for 8 warps");
+  static_assert(KS >= 1 && KS * NG * UW == NW, "warps must factor as NG x UW x KS");
   const int g = warp / (UW * KS), rem = warp % (UW * KS), uw = rem / KS, ks = rem % KS;
   const Gemm& G = (NG == 2 && g == 1) ? g1 : g0;
   const int ul = uw * 32 * U + lane * U;
@@ -190,42 +236,49 @@ __device__ __forceinline__ void wide_partials(float* part, const Gemm& g0, const
   for (int r = 0; r < RT; ++r) ActLoad<U>::st(dst + r * BT, acc[r]);
 }
 
-// Narrow mapping (Bp == G <= 8): lanes stride over float4 columns, RT rows per warp pass, shuffle reduction.
-// Warps [wbeg, wbeg+wcnt) take part.  Result in part[(gslot*NR + r)*G + u].
+// Narrow mapping (Bp == G <= 8): the whole activation vector of the phase is first staged into shared memory by all
+// threads (ONE L2 round trip), then lanes stride over float4 columns, RT rows per warp pass, shuffle reduction.
+// Warps [wbeg, wbeg+wcnt) take part.  Result in out[(gslot*nrows + r)*G + u].
+template <int G>
+__device__ __forceinline__ void smem_ld(const float* p, float (&a)[G]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+  if constexpr (G == 8) {
+    const float4 w = *(reinterpret_cast<const float4*>(p) + 1);
+    a[4] = w.x; a[5] = w.y; a[6] = w.z; a[7] = w.w;
+  }
+}
+template <int NT>
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int nfloats, int tid) {
+  for (int i = tid; i < nfloats / 4; i += NT)
+    reinterpret_cast<float4*>(dst)[i] = __ldcg(reinterpret_cast<const float4*>(src) + i);
+}
 template <int G, int RT>
-__device__ __forceinline__ void narrow_rows(float* part, int gslot, const Gemm& Gm, int nrows, int wbeg, int wcnt, int warp,
-                                            int lane) {
+__device__ __forceinline__ void narrow_rows(float* out, int gslot, const float* __restrict__ W, int ldw, const float* act,
+                                            int n4, int nrows, int wbeg, int wcnt, int warp, int lane) {
   if (warp < wbeg || warp >= wbeg + wcnt) return;
-  const int ldw4 = Gm.ldw >> 2;
+  const int ldw4 = ldw >> 2;
   for (int r0 = (warp - wbeg) * RT; r0 < nrows; r0 += wcnt * RT) {
     float acc[RT][G];
 #pragma unroll
     for (int r = 0; r < RT; ++r)
 #pragma unroll
       for (int u = 0; u < G; ++u) acc[r][u] = 0.f;
-    int col = 0;
+    const float4* W4 = reinterpret_cast<const float4*>(W) + (size_t)r0 * ldw4;
+    for (int c4 = lane; c4 < n4; c4 += 32) {
+      float a[4][G];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (s < Gm.nseg) {
-        const float4* W4 = reinterpret_cast<const float4*>(Gm.W) + (size_t)r0 * ldw4 + col;
-        const float* act = Gm.seg[s].act;
-        for (int c4 = lane; c4 < Gm.seg[s].n4; c4 += 32) {
-          float a[4][G];
+      for (int kk = 0; kk < 4; ++kk) smem_ld<G>(act + (size_t)(4 * c4 + kk) * G, a[kk]);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) ActLoad<G>::ld(act + (size_t)(4 * c4 + kk) * G, a[kk]);
+      for (int r = 0; r < RT; ++r) {
+        float4 w = W4[r * ldw4 + c4];
 #pragma unroll
-          for (int r = 0; r < RT; ++r) {
-            float4 w = W4[r * ldw4 + c4];
-#pragma unroll
-            for (int u = 0; u < G; ++u) {
-              acc[r][u] = fmaf(w.x, a[0][u], acc[r][u]);
-              acc[r][u] = fmaf(w.y, a[1][u], acc[r][u]);
-              acc[r][u] = fmaf(w.z, a[2][u], acc[r][u]);
-              acc[r][u] = fmaf(w.w, a[3][u], acc[r][u]);
-            }
-          }
+        for (int u = 0; u < G; ++u) {
+          acc[r][u] = fmaf(w.x, a[0][u], acc[r][u]);
+          acc[r][u] = fmaf(w.y, a[1][u], acc[r][u]);
+          acc[r][u] = fmaf(w.z, a[2][u], acc[r][u]);
+          acc[r][u] = fmaf(w.w, a[3][u], acc[r][u]);
         }
-        col += Gm.seg[s].n4;
       }
     }
 #pragma unroll
@@ -233,7 +286,7 @@ __device__ __forceinline__ void narrow_rows(float* part, int gslot, const Gemm& 
 #pragma unroll
       for (int u = 0; u < G; ++u) {
         float v = warp_sum(acc[r][u]);
-        if (lane == 0) part[(size_t)(gslot * nrows + r0 + r) * G + u] = v;
+        if (lane == 0) out[(size_t)(gslot * nrows + r0 + r) * G + u] = v;
       }
   }
 }
@@ -241,15 +294,22 @@ __device__ __forceinline__ void narrow_rows(float* part, int gslot, const Gemm& 
 // Mapping traits.  U == 0 selects the narrow mapping with G = UW utterances.
 template <int U, int UW> struct MapTraits {
   static constexpr bool kWide = true;
+  static constexpr int NW = kGridWarpsWide;
   static constexpr int BT = 32 * U * UW;                                   // utterances per tile
-  static constexpr int KS1 = kGridWarps / UW;                              // k slices of a 1-GEMM phase
-  static constexpr int KS2 = kGridWarps / (2 * UW);                        // ... of a 2-GEMM phase
+  static constexpr int KS1 = NW / UW;                                      // k slices of a 1-GEMM phase
+  static constexpr int KS2 = NW / (2 * UW);                                // ... of a 2-GEMM phase
+  static constexpr int kScratchFloats = (NW / UW) * 3 * kUPC * BT;         // partial sums of the largest phase
 };
 template <int G> struct MapTraits<0, G> {
   static constexpr bool kWide = false;
+  static constexpr int NW = kGridWarpsNarrow;
   static constexpr int BT = G;
   static constexpr int KS1 = 1;
   static constexpr int KS2 = 1;
+  static constexpr int kStageA = 0;                                         // [R+AUX][G] staged activation (max 640 rows)
+  static constexpr int kStageB = 640 * G;                                   // [R][G]
+  static constexpr int kOut = kStageB + 512 * G;                            // [2][12][G] row results
+  static constexpr int kScratchFloats = kOut + 2 * 3 * kUPC * G + 64;
 };
 
 // sum over k slices of one output: gemm slot g, row r (of RT), local utterance ul
@@ -261,15 +321,21 @@ __device__ __forceinline__ float part_sum(const float* part, int g, int r, int u
   return v;
 }
 
+__device__ __forceinline__ float gru_update(float gir, float giz, float gin, float ghr, float ghz, float ghn, float hold) {
+  const float r = sigmoidf_acc(gir + ghr), z = sigmoidf_acc(giz + ghz);
+  const float n = tanhf(gin + r * ghn);
+  return (1.0f - z) * n + z * hold;
+}
+
 template <int U, int UW>
-__global__ void __launch_bounds__(kGridThreads, 1) wavernn_grid_kernel(GridModel M, GridArgs A) {
+__global__ void __launch_bounds__(MapTraits<U, UW>::NW * 32, 1) wavernn_grid_kernel(GridModel M, GridArgs A) {
   using MT = MapTraits<U, UW>;
-  constexpr int BT = MT::BT;
-  constexpr int KS1 = MT::KS1;
-  constexpr int KS2 = MT::KS2;
+  constexpr int BT = MT::BT, NW = MT::NW, NT = NW * 32;
+  constexpr int KS1 = MT::KS1, KS2 = MT::KS2;
+  constexpr int G = MT::kWide ? 4 : UW;               // narrow: utterances per row; (unused value in wide mode)
   extern __shared__ __align__(16) float smem[];
   float* Wb = smem;                                   // this CTA's weights, resident for the whole kernel
-  float* part = smem + M.blob;                        // partial sums of the current phase
+  float* part = smem + M.blob;                        // wide: partial sums; narrow: staged activations + row results
   __shared__ float xs[BT > 32 ? BT : 32];             // fed-back sample of the tile's utterances
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -279,7 +345,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) wavernn_grid_kernel(GridModel
   {
     const float4* src = reinterpret_cast<const float4*>(A.wblob + (size_t)c * M.blob);
     float4* dst = reinterpret_cast<float4*>(Wb);
-    for (int i = tid; i < M.blob / 4; i += kGridThreads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < M.blob / 4; i += NT) dst[i] = __ldg(src + i);
   }
   __syncthreads();
   const float* bI = Wb + M.oI_b;
@@ -287,7 +353,24 @@ __global__ void __launch_bounds__(kGridThreads, 1) wavernn_grid_kernel(GridModel
   unsigned int nbar = 0;
   const unsigned int ncta = gridDim.x;
   const size_t RB = (size_t)R * Bp;
+  // narrow-mode scratch views
+  float* stA = part;
+  float* stB = part + (MT::kWide ? 0 : 640 * G);
+  float* nout = part + (MT::kWide ? 0 : 640 * G + 512 * G);
+  const float* res = MT::kWide ? part : nout;         // where part_sum() reads
 
+  long long pf[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) pf[i] = 0;
+  long long tmark = clock64();
+#define PROF_MARK(slot)                                   \
+  do {                                                    \
+    if (A.prof) {                                         \
+      long long now_ = clock64();                         \
+      pf[slot] += now_ - tmark;                           \
+      tmark = now_;                                       \
+    }                                                     \
+  } while (0)
   for (int t = 0; t < A.steps; ++t) {
     const int cur = t & 1, fr = t / A.hop;
     const float* auxT = A.aux_T + (size_t)fr * 4 * AUX * Bp;
@@ -298,7 +381,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) wavernn_grid_kernel(GridModel
 
     // ================= P0: read back the previous step's winner, then the I layer =================
     for (int tb = 0; tb < Bp; tb += BT) {
-      for (int ul = tid; ul < BT; ul += kGridThreads) {
+      for (int ul = tid; ul < BT; ul += NT) {
         const int u = tb + ul;
         float x = 0.f;
         if (t > 0 && u < A.B) {
@@ -310,128 +393,174 @@ __global__ void __launch_bounds__(kGridThreads, 1) wavernn_grid_kernel(GridModel
         }
         xs[ul] = x;
       }
-      Gemm g{};
-      g.W = Wb + M.oI_w; g.ldw = M.ldC; g.nseg = 2;
-      g.seg[0] = Seg{A.mels_T + (size_t)t * M.FEAT * Bp, M.FEAT / 4};
-      g.seg[1] = Seg{auxT, AUX / 4};
-      if constexpr (MT::kWide) wide_partials<U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
-      else narrow_rows<UW, 1>(part, 0, g, kUPC, 0, kGridWarps, warp, lane);
+      const float* melT = A.mels_T + (size_t)t * M.FEAT * Bp;
+      if constexpr (MT::kWide) {
+        Gemm g{};
+        g.W = Wb + M.oI_w; g.ldw = M.ldC; g.nseg = 2;
+        g.seg[0] = Seg{melT, M.FEAT / 4};
+        g.seg[1] = Seg{auxT, AUX / 4};
+        wide_partials<NW, U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
+      } else {
+        stage_rows<NT>(stA, melT, M.FEAT * G, tid);
+        stage_rows<NT>(stA + M.FEAT * G, auxT, AUX * G, tid);
+        __syncthreads();
+        narrow_rows<G, 1>(nout, 0, Wb + M.oI_w, M.ldC, stA, M.ldC / 4, kUPC, 0, NW, warp, lane);
+      }
       __syncthreads();
-      for (int idx = tid; idx < BT * kUPC; idx += kGridThreads) {
+      for (int idx = tid; idx < BT * kUPC; idx += NT) {
         const int ul = idx % BT, j = idx / BT;
-        float v = part_sum<KS1, kUPC, BT>(part, 0, j, ul);
+        float v = part_sum<KS1, kUPC, BT>(res, 0, j, ul);
         v = fmaf(wIx[j], xs[ul], v) + bI[j];
         A.Iout[(size_t)(c * kUPC + j) * Bp + tb + ul] = v;
       }
-      __syncthreads();
+      if (tb + BT < Bp) __syncthreads();
     }
+    PROF_MARK(0);
     if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    PROF_MARK(1);
 
     // ================= P1: GRU 1 =================
     for (int tb = 0; tb < Bp; tb += BT) {
-      Gemm gi{}, gh{};
-      gi.W = Wb + M.oih1; gi.ldw = R; gi.nseg = 1; gi.seg[0] = Seg{A.Iout, R / 4};
-      gh.W = Wb + M.ohh1; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h1c, R / 4};
-      if constexpr (MT::kWide) wide_partials<U, UW, 3 * kUPC, 2>(part, gi, gh, tb, Bp, warp, lane);
-      else {
-        narrow_rows<UW, 3>(part, 0, gi, 3 * kUPC, 0, 4, warp, lane);
-        narrow_rows<UW, 3>(part, 1, gh, 3 * kUPC, 4, 4, warp, lane);
+      if constexpr (MT::kWide) {
+        Gemm gi{}, gh{};
+        gi.W = Wb + M.oih1; gi.ldw = R; gi.nseg = 1; gi.seg[0] = Seg{A.Iout, R / 4};
+        gh.W = Wb + M.ohh1; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h1c, R / 4};
+        wide_partials<NW, U, UW, 3 * kUPC, 2>(part, gi, gh, tb, Bp, warp, lane);
+      } else {
+        stage_rows<NT>(stA, A.Iout, R * G, tid);
+        stage_rows<NT>(stB, h1c, R * G, tid);
+        __syncthreads();
+        narrow_rows<G, 3>(nout, 0, Wb + M.oih1, R, stA, R / 4, 3 * kUPC, 0, NW / 2, warp, lane);
+        narrow_rows<G, 3>(nout, 1, Wb + M.ohh1, R, stB, R / 4, 3 * kUPC, NW / 2, NW / 2, warp, lane);
       }
       __syncthreads();
       const float* bih = Wb + M.obih1; const float* bhh = Wb + M.obhh1;
-      for (int idx = tid; idx < BT * kUPC; idx += kGridThreads) {
+      for (int idx = tid; idx < BT * kUPC; idx += NT) {
         const int ul = idx % BT, j = idx / BT;
         const size_t o = (size_t)(c * kUPC + j) * Bp + tb + ul;
-        float gir = part_sum<KS2, 3 * kUPC, BT>(part, 0, j, ul) + bih[j];
-        float giz = part_sum<KS2, 3 * kUPC, BT>(part, 0, kUPC + j, ul) + bih[kUPC + j];
-        float gin = part_sum<KS2, 3 * kUPC, BT>(part, 0, 2 * kUPC + j, ul) + bih[2 * kUPC + j];
-        float ghr = part_sum<KS2, 3 * kUPC, BT>(part, 1, j, ul) + bhh[j];
-        float ghz = part_sum<KS2, 3 * kUPC, BT>(part, 1, kUPC + j, ul) + bhh[kUPC + j];
-        float ghn = part_sum<KS2, 3 * kUPC, BT>(part, 1, 2 * kUPC + j, ul) + bhh[2 * kUPC + j];
-        float r = sigmoidf_acc(gir + ghr), z = sigmoidf_acc(giz + ghz);
-        float n = tanhf(gin + r * ghn);
-        float h = (1.0f - z) * n + z * __ldcg(h1c + o);
+        float hold, resid;
+        if constexpr (MT::kWide) { hold = __ldcg(h1c + o); resid = __ldcg(A.Iout + o); }
+        else { hold = stB[(c * kUPC + j) * G + ul]; resid = stA[(c * kUPC + j) * G + ul]; }
+        float h = gru_update(part_sum<KS2, 3 * kUPC, BT>(res, 0, j, ul) + bih[j],
+                             part_sum<KS2, 3 * kUPC, BT>(res, 0, kUPC + j, ul) + bih[kUPC + j],
+                             part_sum<KS2, 3 * kUPC, BT>(res, 0, 2 * kUPC + j, ul) + bih[2 * kUPC + j],
+                             part_sum<KS2, 3 * kUPC, BT>(res, 1, j, ul) + bhh[j],
+                             part_sum<KS2, 3 * kUPC, BT>(res, 1, kUPC + j, ul) + bhh[kUPC + j],
+                             part_sum<KS2, 3 * kUPC, BT>(res, 1, 2 * kUPC + j, ul) + bhh[2 * kUPC + j], hold);
         h1n[o] = h;
-        A.x1[o] = __ldcg(A.Iout + o) + h;
+        A.x1[o] = resid + h;
       }
-      __syncthreads();
+      if (tb + BT < Bp) __syncthreads();
     }
+    PROF_MARK(2);
     if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    PROF_MARK(3);
 
     // ================= P2: GRU 2 =================
     for (int tb = 0; tb < Bp; tb += BT) {
-      Gemm gi{}, gh{};
-      gi.W = Wb + M.oih2; gi.ldw = M.ldX; gi.nseg = 2; gi.seg[0] = Seg{A.x1, R / 4}; gi.seg[1] = Seg{auxT + (size_t)AUX * Bp, AUX / 4};
-      gh.W = Wb + M.ohh2; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h2c, R / 4};
-      if constexpr (MT::kWide) wide_partials<U, UW, 3 * kUPC, 2>(part, gi, gh, tb, Bp, warp, lane);
-      else {
-        narrow_rows<UW, 3>(part, 0, gi, 3 * kUPC, 0, 4, warp, lane);
-        narrow_rows<UW, 3>(part, 1, gh, 3 * kUPC, 4, 4, warp, lane);
+      if constexpr (MT::kWide) {
+        Gemm gi{}, gh{};
+        gi.W = Wb + M.oih2; gi.ldw = M.ldX; gi.nseg = 2; gi.seg[0] = Seg{A.x1, R / 4};
+        gi.seg[1] = Seg{auxT + (size_t)AUX * Bp, AUX / 4};
+        gh.W = Wb + M.ohh2; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h2c, R / 4};
+        wide_partials<NW, U, UW, 3 * kUPC, 2>(part, gi, gh, tb, Bp, warp, lane);
+      } else {
+        stage_rows<NT>(stA, A.x1, R * G, tid);
+        stage_rows<NT>(stA + R * G, auxT + (size_t)AUX * Bp, AUX * G, tid);
+        stage_rows<NT>(stB, h2c, R * G, tid);
+        __syncthreads();
+        narrow_rows<G, 3>(nout, 0, Wb + M.oih2, M.ldX, stA, M.ldX / 4, 3 * kUPC, 0, NW / 2, warp, lane);
+        narrow_rows<G, 3>(nout, 1, Wb + M.ohh2, R, stB, R / 4, 3 * kUPC, NW / 2, NW / 2, warp, lane);
       }
       __syncthreads();
       const float* bih = Wb + M.obih2; const float* bhh = Wb + M.obhh2;
-      for (int idx = tid; idx < BT * kUPC; idx += kGridThreads) {
+      for (int idx = tid; idx < BT * kUPC; idx += NT) {
         const int ul = idx % BT, j = idx / BT;
         const size_t o = (size_t)(c * kUPC + j) * Bp + tb + ul;
-        float gir = part_sum<KS2, 3 * kUPC, BT>(part, 0, j, ul) + bih[j];
-        float giz = part_sum<KS2, 3 * kUPC, BT>(part, 0, kUPC + j, ul) + bih[kUPC + j];
-        float gin = part_sum<KS2, 3 * kUPC, BT>(part, 0, 2 * kUPC + j, ul) + bih[2 * kUPC + j];
-        float ghr = part_sum<KS2, 3 * kUPC, BT>(part, 1, j, ul) + bhh[j];
-        float ghz = part_sum<KS2, 3 * kUPC, BT>(part, 1, kUPC + j, ul) + bhh[kUPC + j];
-        float ghn = part_sum<KS2, 3 * kUPC, BT>(part, 1, 2 * kUPC + j, ul) + bhh[2 * kUPC + j];
-        float r = sigmoidf_acc(gir + ghr), z = sigmoidf_acc(giz + ghz);
-        float n = tanhf(gin + r * ghn);
-        float h = (1.0f - z) * n + z * __ldcg(h2c + o);
+        float hold, resid;
+        if constexpr (MT::kWide) { hold = __ldcg(h2c + o); resid = __ldcg(A.x1 + o); }
+        else { hold = stB[(c * kUPC + j) * G + ul]; resid = stA[(c * kUPC + j) * G + ul]; }
+        float h = gru_update(part_sum<KS2, 3 * kUPC, BT>(res, 0, j, ul) + bih[j],
+                             part_sum<KS2, 3 * kUPC, BT>(res, 0, kUPC + j, ul) + bih[kUPC + j],
+                             part_sum<KS2, 3 * kUPC, BT>(res, 0, 2 * kUPC + j, ul) + bih[2 * kUPC + j],
+                             part_sum<KS2, 3 * kUPC, BT>(res, 1, j, ul) + bhh[j],
+                             part_sum<KS2, 3 * kUPC, BT>(res, 1, kUPC + j, ul) + bhh[kUPC + j],
+                             part_sum<KS2, 3 * kUPC, BT>(res, 1, 2 * kUPC + j, ul) + bhh[2 * kUPC + j], hold);
         h2n[o] = h;
-        A.x2[o] = __ldcg(A.x1 + o) + h;
+        A.x2[o] = resid + h;
       }
-      __syncthreads();
+      if (tb + BT < Bp) __syncthreads();
     }
+    PROF_MARK(4);
     if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    PROF_MARK(5);
 
     // ================= P3: fc1 + relu  (CTA 0 also recycles the argmax slot the NEXT step will use) =================
     if (c == 0)
-      for (int u = tid; u < Bp; u += kGridThreads) A.best[(size_t)((t + 1) & 1) * Bp + u] = 0ull;
+      for (int u = tid; u < Bp; u += NT) A.best[(size_t)((t + 1) & 1) * Bp + u] = 0ull;
     for (int tb = 0; tb < Bp; tb += BT) {
-      Gemm g{};
-      g.W = Wb + M.ofc1; g.ldw = M.ldX; g.nseg = 2; g.seg[0] = Seg{A.x2, R / 4}; g.seg[1] = Seg{auxT + (size_t)2 * AUX * Bp, AUX / 4};
-      if constexpr (MT::kWide) wide_partials<U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
-      else narrow_rows<UW, 1>(part, 0, g, kUPC, 0, kGridWarps, warp, lane);
-      __syncthreads();
-      const float* b = Wb + M.obfc1;
-      for (int idx = tid; idx < BT * kUPC; idx += kGridThreads) {
-        const int ul = idx % BT, j = idx / BT;
-        A.f1[(size_t)(c * kUPC + j) * Bp + tb + ul] = fmaxf(part_sum<KS1, kUPC, BT>(part, 0, j, ul) + b[j], 0.f);
+      if constexpr (MT::kWide) {
+        Gemm g{};
+        g.W = Wb + M.ofc1; g.ldw = M.ldX; g.nseg = 2; g.seg[0] = Seg{A.x2, R / 4};
+        g.seg[1] = Seg{auxT + (size_t)2 * AUX * Bp, AUX / 4};
+        wide_partials<NW, U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
+      } else {
+        stage_rows<NT>(stA, A.x2, R * G, tid);
+        stage_rows<NT>(stA + R * G, auxT + (size_t)2 * AUX * Bp, AUX * G, tid);
+        __syncthreads();
+        narrow_rows<G, 1>(nout, 0, Wb + M.ofc1, M.ldX, stA, M.ldX / 4, kUPC, 0, NW, warp, lane);
       }
       __syncthreads();
+      const float* b = Wb + M.obfc1;
+      for (int idx = tid; idx < BT * kUPC; idx += NT) {
+        const int ul = idx % BT, j = idx / BT;
+        A.f1[(size_t)(c * kUPC + j) * Bp + tb + ul] = fmaxf(part_sum<KS1, kUPC, BT>(res, 0, j, ul) + b[j], 0.f);
+      }
+      if (tb + BT < Bp) __syncthreads();
     }
+    PROF_MARK(6);
     if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    PROF_MARK(7);
 
     // ================= P4: fc2 + relu =================
     for (int tb = 0; tb < Bp; tb += BT) {
-      Gemm g{};
-      g.W = Wb + M.ofc2; g.ldw = M.ldF; g.nseg = 2; g.seg[0] = Seg{A.f1, F / 4}; g.seg[1] = Seg{auxT + (size_t)3 * AUX * Bp, AUX / 4};
-      if constexpr (MT::kWide) wide_partials<U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
-      else narrow_rows<UW, 1>(part, 0, g, kUPC, 0, kGridWarps, warp, lane);
-      __syncthreads();
-      const float* b = Wb + M.obfc2;
-      for (int idx = tid; idx < BT * kUPC; idx += kGridThreads) {
-        const int ul = idx % BT, j = idx / BT;
-        A.f2[(size_t)(c * kUPC + j) * Bp + tb + ul] = fmaxf(part_sum<KS1, kUPC, BT>(part, 0, j, ul) + b[j], 0.f);
+      if constexpr (MT::kWide) {
+        Gemm g{};
+        g.W = Wb + M.ofc2; g.ldw = M.ldF; g.nseg = 2; g.seg[0] = Seg{A.f1, F / 4};
+        g.seg[1] = Seg{auxT + (size_t)3 * AUX * Bp, AUX / 4};
+        wide_partials<NW, U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
+      } else {
+        stage_rows<NT>(stA, A.f1, F * G, tid);
+        stage_rows<NT>(stA + F * G, auxT + (size_t)3 * AUX * Bp, AUX * G, tid);
+        __syncthreads();
+        narrow_rows<G, 1>(nout, 0, Wb + M.ofc2, M.ldF, stA, M.ldF / 4, kUPC, 0, NW, warp, lane);
       }
       __syncthreads();
+      const float* b = Wb + M.obfc2;
+      for (int idx = tid; idx < BT * kUPC; idx += NT) {
+        const int ul = idx % BT, j = idx / BT;
+        A.f2[(size_t)(c * kUPC + j) * Bp + tb + ul] = fmaxf(part_sum<KS1, kUPC, BT>(res, 0, j, ul) + b[j], 0.f);
+      }
+      if (tb + BT < Bp) __syncthreads();
     }
+    PROF_MARK(8);
     if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    PROF_MARK(9);
 
     // ================= P5: fc3 + distributed Gumbel-max sampling =================
     for (int tb = 0; tb < Bp; tb += BT) {
-      Gemm g{};
-      g.W = Wb + M.ofc3; g.ldw = F; g.nseg = 1; g.seg[0] = Seg{A.f2, F / 4};
-      if constexpr (MT::kWide) wide_partials<U, UW, kCPC, 1>(part, g, g, tb, Bp, warp, lane);
-      else narrow_rows<UW, 1>(part, 0, g, kCPC, 0, kGridWarps, warp, lane);
+      if constexpr (MT::kWide) {
+        Gemm g{};
+        g.W = Wb + M.ofc3; g.ldw = F; g.nseg = 1; g.seg[0] = Seg{A.f2, F / 4};
+        wide_partials<NW, U, UW, kCPC, 1>(part, g, g, tb, Bp, warp, lane);
+      } else {
+        stage_rows<NT>(stA, A.f2, F * G, tid);
+        __syncthreads();
+        narrow_rows<G, 1>(nout, 0, Wb + M.ofc3, F, stA, F / 4, kCPC, 0, NW, warp, lane);
+      }
       __syncthreads();
       const float* b = Wb + M.obfc3;
-      for (int ul = tid; ul < BT; ul += kGridThreads) {
+      for (int ul = tid; ul < BT; ul += NT) {
         const int u = tb + ul;
         if (u < A.B) {
           unsigned long long bestp = 0ull;
@@ -448,7 +577,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) wavernn_grid_kernel(GridModel
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int r = r4 * 4 + k;
-              float l = part_sum<KS1, kCPC, BT>(part, 0, r, ul) + b[r];
+              float l = part_sum<KS1, kCPC, BT>(res, 0, r, ul) + b[r];
               if (A.logits_out) A.logits_out[((size_t)t * A.B + u) * M.NC + cls0 + k] = l;
               unsigned long long p = pack_key(l - logf(q[k]), (uint32_t)(cls0 + k));
               bestp = p > bestp ? p : bestp;
@@ -457,14 +586,19 @@ __global__ void __launch_bounds__(kGridThreads, 1) wavernn_grid_kernel(GridModel
           atomicMax(A.best + (size_t)(t & 1) * Bp + u, bestp);
         }
       }
-      __syncthreads();
+      if (tb + BT < Bp) __syncthreads();
     }
+    PROF_MARK(10);
     if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    PROF_MARK(11);
   }
+  if (A.prof && tid == 0)
+    for (int i = 0; i < 12; ++i) A.prof[(size_t)c * 12 + i] = pf[i];
+#undef PROF_MARK
   // the last step's winner
   if (c == 0 && A.steps > 0) {
     const int t = A.steps;
-    for (int u = tid; u < A.B; u += kGridThreads) {
+    for (int u = tid; u < A.B; u += NT) {
       unsigned long long pk = __ldcg(A.best + (size_t)((t - 1) & 1) * Bp + u);
       A.labels[(size_t)u * A.S + (t - 1)] = (int16_t)unpack_idx(pk);
     }

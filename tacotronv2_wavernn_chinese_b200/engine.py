@@ -180,6 +180,12 @@ class WaveRNNEngine:
                                                            B, step0, n_steps, self.n_classes, _ptr(q), self._stream()))
         return q
 
+    def debug_phase_cycles(self):
+        """[6][2] mean cycles (compute, barrier) per phase of the last grid launch; needs B200TTS_GRID_PROF=1."""
+        out = (C.c_double * 12)()
+        _lib.check(self.lib.b200tts_wavernn_debug_phase_cycles(self._h, out))
+        return np.array(list(out)).reshape(6, 2)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.b200tts_wavernn_launch_count(self._h))

@@ -15,4 +15,7 @@ for k in kernels:
         for it in range(2):
             eng.generate(mels, seed=1, kernel=k, max_steps=steps, want_wave=False)
             ms = eng.last_kernel_ms()
+        if os.environ.get('B200TTS_GRID_PROF') and k == 'grid':
+            pc = eng.debug_phase_cycles() / steps
+            print('   cycles/step per phase (compute, barrier):', ' | '.join(f'P{i}: {a:.0f},{b:.0f}' for i, (a, b) in enumerate(pc)), f' total {pc.sum():.0f}')
         print(f'kernel={k} B={B} steps={steps}: {ms:.1f} ms -> {ms*1e3/steps:.1f} us/step, {B*steps/ms*1e3/1e6:.3f} M samples/s', flush=True)
