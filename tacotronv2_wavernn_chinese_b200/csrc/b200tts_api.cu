@@ -364,7 +364,7 @@ extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b
     g.obih1 = take(3 * kUPC); g.obhh1 = take(3 * kUPC); g.obih2 = take(3 * kUPC); g.obhh2 = take(3 * kUPC);
     g.obfc1 = take(kUPC); g.obfc2 = take(kUPC); g.obfc3 = take(kCPC);
     g.blob = off;
-    size_t smem_need = ((size_t)g.blob + (size_t)MapTraits<4, 2>::kScratchFloats) * sizeof(float) + 2048;
+    size_t smem_need = ((size_t)g.blob + (size_t)MapTraits<4, 2, 1>::kScratchFloats) * sizeof(float) + 2048;
     if (smem_need > 227 * 1024) g.ok = 0;
     B200_CUDA(cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, device));
     if (!ctx->coop) g.ok = 0;
@@ -513,13 +513,13 @@ static void launch_utt(b200tts_wavernn* ctx, const GenArgs& a, cudaStream_t st) 
   ctx->launches++;
 }
 
-template <int U, int UW>
+template <int U, int UW, int GROUPS>
 static void launch_grid_t(b200tts_wavernn* ctx, GridArgs& a, cudaStream_t st) {
   const GridModel& g = ctx->gm;
-  using MT = MapTraits<U, UW>;
+  using MT = MapTraits<U, UW, GROUPS>;
   constexpr int kThreads = MT::NW * 32;
   size_t smem = ((size_t)g.blob + (size_t)MT::kScratchFloats) * sizeof(float);
-  auto kern = wavernn_grid_kernel<U, UW>;
+  auto kern = wavernn_grid_kernel<U, UW, GROUPS>;
   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
@@ -530,25 +530,27 @@ static void launch_grid_t(b200tts_wavernn* ctx, GridArgs& a, cudaStream_t st) {
   ctx->launches++;
 }
 
-// returns the padded batch the grid kernel will use for B utterances
-static int grid_padded_batch(int B, int* U, int* UW) {
-  if (B <= 4) { *U = 0; *UW = 4; return 4; }
-  if (B <= 8) { *U = 0; *UW = 8; return 8; }
-  if (B <= 32) { *U = 1; *UW = 1; return 32; }
-  if (B <= 64) { *U = 2; *UW = 1; return 64; }
-  if (B <= 128) { *U = 4; *UW = 1; return 128; }
-  int p256 = (B + 255) / 256 * 256, p128 = (B + 127) / 128 * 128;
-  if (p128 < p256) { *U = 4; *UW = 1; return p128; }
-  *U = 4; *UW = 2; return p256;
+// Mapping for B utterances: returns the padded batch; variant = index into the dispatch table below.
+enum { GV_N4, GV_N8, GV_W1, GV_W1x2, GV_W2x2, GV_W4x2, GV_W4_2 };
+static int grid_variant(int B, int* variant) {
+  static const bool single = getenv("B200TTS_GRID_SINGLE_GROUP") != nullptr;   // A/B switch for measurements
+  if (B <= 4) { *variant = GV_N4; return 4; }
+  if (B <= 8) { *variant = GV_N8; return 8; }
+  if (B <= 32) { *variant = GV_W1; return 32; }
+  if (single) { *variant = GV_W4_2; return (B + 255) / 256 * 256; }
+  if (B <= 64) { *variant = GV_W1x2; return 64; }
+  if (B <= 128) { *variant = GV_W2x2; return 128; }
+  *variant = GV_W4x2;
+  return (B + 255) / 256 * 256;
 }
 
 static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cudaStream_t st) {
   const b200tts_wavernn_cfg& c = ctx->cfg;
   const GridModel& g = ctx->gm;
   REQUIRE(g.ok, B200TTS_EINVAL, "this model/device cannot run the grid kernel (use B200TTS_KERNEL_UTTERANCE)");
-  int U = 0, UW = 0;
+  int variant = 0;
   const int B = ua.B, T = ua.T, S = ua.S, O = c.res_out_dims;
-  const int Bp = grid_padded_batch(B, &U, &UW);
+  const int Bp = grid_variant(B, &variant);
   // conditioning in K-major layout
   ctx->mels_T.ensure((size_t)S * c.feat_dims * Bp * sizeof(float));
   ctx->aux_T.ensure((size_t)T * O * Bp * sizeof(float));
@@ -567,7 +569,7 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   // activations + sync words, zero-initialised (h1 = h2 = 0, fatchord_version.py:194-195)
   const size_t RB = (size_t)g.R * Bp;
   const size_t act_floats = 9 * RB;
-  const size_t sync_bytes = 2 * (size_t)Bp * sizeof(unsigned long long) + 256;
+  const size_t sync_bytes = 2 * (size_t)Bp * sizeof(unsigned long long) + 512;
   ctx->grid_scratch.ensure(act_floats * sizeof(float));
   ctx->grid_sync.ensure(sync_bytes);
   B200_CUDA(cudaMemsetAsync(ctx->grid_scratch.p, 0, act_floats * sizeof(float), st));
@@ -579,7 +581,7 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   a.f1 = base + 7 * RB; a.f2 = base + 8 * RB;
   a.best = ctx->grid_sync.as<unsigned long long>();
   a.barrier = reinterpret_cast<unsigned int*>(ctx->grid_sync.as<char>() + 2 * (size_t)Bp * sizeof(unsigned long long));
-  a.error = reinterpret_cast<int*>(a.barrier + 16);
+  a.error = reinterpret_cast<int*>(a.barrier + 96);
   a.mels_T = ctx->mels_T.as<float>();
   a.aux_T = ctx->aux_T.as<float>();
   a.B = B; a.Bp = Bp; a.S = S; a.T = T; a.hop = ua.hop; a.steps = ua.steps;
@@ -593,12 +595,15 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
     ctx->last_grid_ncta = g.ncta;
   }
   B200_CUDA(cudaEventRecord(ctx->ev0, st));
-  if (U == 0 && UW == 4) launch_grid_t<0, 4>(ctx, a, st);
-  else if (U == 0) launch_grid_t<0, 8>(ctx, a, st);
-  else if (U == 1) launch_grid_t<1, 1>(ctx, a, st);
-  else if (U == 2) launch_grid_t<2, 1>(ctx, a, st);
-  else if (UW == 1) launch_grid_t<4, 1>(ctx, a, st);
-  else launch_grid_t<4, 2>(ctx, a, st);
+  switch (variant) {
+    case GV_N4: launch_grid_t<0, 4, 1>(ctx, a, st); break;
+    case GV_N8: launch_grid_t<0, 8, 1>(ctx, a, st); break;
+    case GV_W1: launch_grid_t<1, 1, 1>(ctx, a, st); break;
+    case GV_W1x2: launch_grid_t<1, 1, 2>(ctx, a, st); break;
+    case GV_W2x2: launch_grid_t<2, 1, 2>(ctx, a, st); break;
+    case GV_W4x2: launch_grid_t<4, 1, 2>(ctx, a, st); break;
+    default: launch_grid_t<4, 2, 1>(ctx, a, st); break;
+  }
   B200_CUDA(cudaEventRecord(ctx->ev1, st));
 }
 

@@ -81,12 +81,21 @@ __device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned in
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// All threads call.  `target` = (number of barriers passed so far + 1) * gridDim.x.  Returns false on timeout.
-__device__ __forceinline__ bool grid_barrier(unsigned int* ctr, unsigned int target, int* error) {
-  __shared__ int s_ok;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    red_release_add_u32(ctr, 1u);                 // release: orders this CTA's prior global writes (cumulative via bar.sync)
+// Group-local block barrier: the CTA may host two independent utterance groups (warps [0,NWG) and [NWG,2*NWG)); each
+// synchronises on its own named barrier so that one group can sit in a grid barrier while the other computes.
+template <int GROUPS, int NTG>
+__device__ __forceinline__ void group_sync(int grp) {
+  if constexpr (GROUPS == 1) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NTG) : "memory");
+}
+
+// All threads of the group call.  `target` = (number of barriers passed so far + 1) * gridDim.x.  False on timeout.
+template <int GROUPS, int NTG>
+__device__ __forceinline__ bool grid_barrier(unsigned int* ctr, unsigned int target, int* error, int grp, int gtid) {
+  __shared__ int s_ok[2];
+  group_sync<GROUPS, NTG>(grp);
+  if (gtid == 0) {
+    red_release_add_u32(ctr, 1u);                 // release: orders this group's prior global writes (cumulative via bar.sync)
     int ok = 1;
     long long t0 = clock64();
     while (ld_acquire_u32(ctr) < target) {
@@ -96,10 +105,10 @@ __device__ __forceinline__ bool grid_barrier(unsigned int* ctr, unsigned int tar
         break;
       }
     }
-    s_ok = ok;
+    s_ok[grp] = ok;
   }
-  __syncthreads();
-  return s_ok != 0;
+  group_sync<GROUPS, NTG>(grp);
+  return s_ok[grp] != 0;
 }
 
 // ---- activation loads (L2 only: these buffers are rewritten by other SMs every step) ----------------------------------
@@ -160,52 +169,72 @@ __device__ __forceinline__ void wide_fma4(float (&acc)[RT][U], const float4* __r
   }
 }
 template <int U>
-__device__ __forceinline__ void wide_ld4(float (&a)[4][U], const float* __restrict__ act, size_t Bp, int c4, int hi) {
-  if (c4 < hi) {
+__device__ __forceinline__ void wide_ld4(float (&a)[4][U], const float* __restrict__ p, unsigned Bp) {
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) ActLoad<U>::ld(act + (size_t)(4 * c4 + kk) * Bp, a[kk]);
+  for (int kk = 0; kk < 4; ++kk) ActLoad<U>::ld(p + kk * Bp, a[kk]);
+}
+// n float4 weight columns starting at W4 (row stride ldw4), activation rows starting at `ap` (row stride Bp floats).
+// Steady state: the loads of the NEXT PD columns are issued before the PD x 4*RT*U FMAs of the current ones (ping-pong
+// register buffers, 4*PD LDG.128 in flight per thread), addresses advance by pointer bumps.
+template <int U, int RT, int PD>
+__device__ __forceinline__ void wide_accumulate_pd(float (&acc)[RT][U], const float* __restrict__ W, int ldw, int col4,
+                                                   const float* __restrict__ act, int Bp_, int u0, int lo, int hi) {
+  const unsigned Bp = (unsigned)Bp_;
+  const int ldw4 = ldw >> 2;
+  const float4* W4 = reinterpret_cast<const float4*>(W) + col4 + lo;
+  const float* p = act + (size_t)(4 * lo) * Bp + u0;
+  const size_t step = (size_t)4 * Bp;
+  const int n = hi - lo;
+  float c[PD][4][U], nb[PD][4][U];
+  int i = 0;
+  if (n >= PD) {
+#pragma unroll
+    for (int j = 0; j < PD; ++j) wide_ld4<U>(c[j], p + j * step, Bp);
+    p += PD * step;
+    for (; i + 3 * PD <= n; i += 2 * PD) {
+#pragma unroll
+      for (int j = 0; j < PD; ++j) wide_ld4<U>(nb[j], p + j * step, Bp);
+      p += PD * step;
+#pragma unroll
+      for (int j = 0; j < PD; ++j) wide_fma4<U, RT>(acc, W4, ldw4, i + j, c[j]);
+#pragma unroll
+      for (int j = 0; j < PD; ++j) wide_ld4<U>(c[j], p + j * step, Bp);
+      p += PD * step;
+#pragma unroll
+      for (int j = 0; j < PD; ++j) wide_fma4<U, RT>(acc, W4, ldw4, i + PD + j, nb[j]);
+    }
+    if (i + 2 * PD <= n) {
+#pragma unroll
+      for (int j = 0; j < PD; ++j) wide_ld4<U>(nb[j], p + j * step, Bp);
+      p += PD * step;
+#pragma unroll
+      for (int j = 0; j < PD; ++j) wide_fma4<U, RT>(acc, W4, ldw4, i + j, c[j]);
+#pragma unroll
+      for (int j = 0; j < PD; ++j) wide_fma4<U, RT>(acc, W4, ldw4, i + PD + j, nb[j]);
+      i += 2 * PD;
+    } else {
+#pragma unroll
+      for (int j = 0; j < PD; ++j) wide_fma4<U, RT>(acc, W4, ldw4, i + j, c[j]);
+      i += PD;
+    }
+  }
+#pragma unroll 1
+  for (; i < n; ++i) {
+    wide_ld4<U>(c[0], p, Bp); p += step;
+    wide_fma4<U, RT>(acc, W4, ldw4, i, c[0]);
   }
 }
 template <int U, int RT>
 __device__ __forceinline__ void wide_accumulate(float (&acc)[RT][U], const float* __restrict__ W, int ldw, int col4,
                                                 const float* __restrict__ act, int Bp, int u0, int lo, int hi) {
-  const float4* W4 = reinterpret_cast<const float4*>(W) + col4;
-  const int ldw4 = ldw >> 2;
-  const float* ap = act + u0;
-#if B200_GRID_PF == 2
-  float a0[4][U], a1[4][U], a2[4][U];
-  wide_ld4<U>(a0, ap, Bp, lo, hi);
-  wide_ld4<U>(a1, ap, Bp, lo + 1, hi);
-  for (int c4 = lo; c4 < hi; c4 += 3) {
-    wide_ld4<U>(a2, ap, Bp, c4 + 2, hi);
-    wide_fma4<U, RT>(acc, W4, ldw4, c4, a0);
-    wide_ld4<U>(a0, ap, Bp, c4 + 3, hi);
-    if (c4 + 1 < hi) wide_fma4<U, RT>(acc, W4, ldw4, c4 + 1, a1);
-    wide_ld4<U>(a1, ap, Bp, c4 + 4, hi);
-    if (c4 + 2 < hi) wide_fma4<U, RT>(acc, W4, ldw4, c4 + 2, a2);
-  }
-#elif B200_GRID_PF == 0
-#pragma unroll 2
-  for (int c4 = lo; c4 < hi; ++c4) {
-    float a[4][U];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) ActLoad<U>::ld(ap + (size_t)(4 * c4 + kk) * Bp, a[kk]);
-    wide_fma4<U, RT>(acc, W4, ldw4, c4, a);
-  }
-#else
-  float a0[4][U], a1[4][U];
-  wide_ld4<U>(a0, ap, Bp, lo, hi);
-  for (int c4 = lo; c4 < hi; c4 += 2) {
-    wide_ld4<U>(a1, ap, Bp, c4 + 1, hi);
-    wide_fma4<U, RT>(acc, W4, ldw4, c4, a0);
-    wide_ld4<U>(a0, ap, Bp, c4 + 2, hi);
-    if (c4 + 1 < hi) wide_fma4<U, RT>(acc, W4, ldw4, c4 + 1, a1);
-  }
-#endif
+  constexpr int PD = 2;   // measured on B200: 3-4 columns ahead on the 4/8-row tiles is SLOWER (19.0k vs 15.5k cycles for fc1)
+  wide_accumulate_pd<U, RT, PD>(acc, W, ldw, col4, act, Bp, u0, lo, hi);
 }
 
 // Wide mapping: NG GEMMs of RT rows each; 8 warps = NG x UW (utterance warps) x KS (k slices).
 // Partial sums land in part[((g*KS + ks)*RT + r)*BT + ul].
+// (Measured: sharing one __noinline__ copy of this body between phases to shrink the ~65 KB kernel is SLOWER, 104.9 vs
+// 97.8 us per lock-step at B=256 -- the call/stack traffic costs more than the instruction-fetch stalls it removes.)
 template <int NW, int U, int UW, int RT, int NG>
 __device__ __forceinline__ void wide_partials(float* part, const Gemm& g0, const Gemm& g1, int tile_base, int Bp, int warp,
                                               int lane) {
@@ -291,25 +320,30 @@ __device__ __forceinline__ void narrow_rows(float* out, int gslot, const float* 
   }
 }
 
-// Mapping traits.  U == 0 selects the narrow mapping with G = UW utterances.
-template <int U, int UW> struct MapTraits {
+// Mapping traits.  U == 0 selects the narrow mapping with G = UW utterances.  GROUPS = independent utterance groups
+// per CTA (wide only): with 2, warps 0-3 and 4-7 run the same phase sequence on disjoint utterance ranges, each with its
+// own named barrier and grid-barrier counter, sharing the resident weights -- stalls of one group (L2 latency, barrier
+// wait) are filled by the other (one warp of each group per scheduler).
+template <int U, int UW, int GROUPS> struct MapTraits {
   static constexpr bool kWide = true;
-  static constexpr int NW = kGridWarpsWide;
-  static constexpr int BT = 32 * U * UW;                                   // utterances per tile
-  static constexpr int KS1 = NW / UW;                                      // k slices of a 1-GEMM phase
-  static constexpr int KS2 = NW / (2 * UW);                                // ... of a 2-GEMM phase
-  static constexpr int kScratchFloats = (NW / UW) * 3 * kUPC * BT;         // partial sums of the largest phase
+  static constexpr int NW = kGridWarpsWide;                                // warps per CTA
+  static constexpr int NWG = NW / GROUPS;                                  // warps per group
+  static constexpr int BT = 32 * U * UW;                                   // utterances per group tile
+  static constexpr int KS1 = NWG / UW;                                     // k slices of a 1-GEMM phase
+  static constexpr int KS2 = NWG / (2 * UW);                               // ... of a 2-GEMM phase
+  static constexpr int kGroupScratch = (NWG / UW) * 3 * kUPC * BT;         // partial sums of the largest phase, per group
+  static constexpr int kScratchFloats = GROUPS * kGroupScratch;
+  static_assert(KS2 >= 1 && KS2 * 2 * UW == NWG, "group warps must factor as 2 x UW x KS2");
 };
-template <int G> struct MapTraits<0, G> {
+template <int G> struct MapTraits<0, G, 1> {
   static constexpr bool kWide = false;
   static constexpr int NW = kGridWarpsNarrow;
+  static constexpr int NWG = NW;
   static constexpr int BT = G;
   static constexpr int KS1 = 1;
   static constexpr int KS2 = 1;
-  static constexpr int kStageA = 0;                                         // [R+AUX][G] staged activation (max 640 rows)
-  static constexpr int kStageB = 640 * G;                                   // [R][G]
-  static constexpr int kOut = kStageB + 512 * G;                            // [2][12][G] row results
-  static constexpr int kScratchFloats = kOut + 2 * 3 * kUPC * G + 64;
+  static constexpr int kGroupScratch = 640 * G + 512 * G + 2 * 3 * kUPC * G + 64;   // staged act A | act B | row results
+  static constexpr int kScratchFloats = kGroupScratch;
 };
 
 // sum over k slices of one output: gemm slot g, row r (of RT), local utterance ul
@@ -327,25 +361,31 @@ __device__ __forceinline__ float gru_update(float gir, float giz, float gin, flo
   return (1.0f - z) * n + z * hold;
 }
 
-template <int U, int UW>
-__global__ void __launch_bounds__(MapTraits<U, UW>::NW * 32, 1) wavernn_grid_kernel(GridModel M, GridArgs A) {
-  using MT = MapTraits<U, UW>;
-  constexpr int BT = MT::BT, NW = MT::NW, NT = NW * 32;
+template <int U, int UW, int GROUPS>
+__global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_grid_kernel(GridModel M, GridArgs A) {
+  using MT = MapTraits<U, UW, GROUPS>;
+  constexpr int BT = MT::BT, NWG = MT::NWG, NT = NWG * 32;   // NT = threads of one group
   constexpr int KS1 = MT::KS1, KS2 = MT::KS2;
   constexpr int G = MT::kWide ? 4 : UW;               // narrow: utterances per row; (unused value in wide mode)
   extern __shared__ __align__(16) float smem[];
   float* Wb = smem;                                   // this CTA's weights, resident for the whole kernel
-  float* part = smem + M.blob;                        // wide: partial sums; narrow: staged activations + row results
-  __shared__ float xs[BT > 32 ? BT : 32];             // fed-back sample of the tile's utterances
+  __shared__ float xs_all[GROUPS * (BT > 32 ? BT : 32)];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31;
+  const int grp = (GROUPS == 1) ? 0 : (int)(threadIdx.x >> 5) / NWG;   // utterance group of this warp
+  const int warp = (int)(threadIdx.x >> 5) - grp * NWG;                // warp index within the group
+  const int tid = (int)threadIdx.x - grp * NT;                         // thread index within the group
+  float* part = smem + M.blob + grp * MT::kGroupScratch;               // wide: partial sums; narrow: staged act + results
+  float* xs = xs_all + grp * (BT > 32 ? BT : 32);                      // fed-back sample of the tile's utterances
   const int c = blockIdx.x, Bp = A.Bp;
+  const int tb_lo = grp * (Bp / GROUPS), tb_hi = (grp + 1) * (Bp / GROUPS);   // this group's utterance columns
+  unsigned int* bar_ctr = A.barrier + grp * 32;
   const int R = M.R, F = M.F, AUX = M.AUX;
   const float ncls_m1 = (float)(M.NC - 1);
   {
     const float4* src = reinterpret_cast<const float4*>(A.wblob + (size_t)c * M.blob);
     float4* dst = reinterpret_cast<float4*>(Wb);
-    for (int i = tid; i < M.blob / 4; i += NT) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < M.blob / 4; i += GROUPS * NT) dst[i] = __ldg(src + i);
   }
   __syncthreads();
   const float* bI = Wb + M.oI_b;
@@ -365,7 +405,7 @@ __global__ void __launch_bounds__(MapTraits<U, UW>::NW * 32, 1) wavernn_grid_ker
   long long tmark = clock64();
 #define PROF_MARK(slot)                                   \
   do {                                                    \
-    if (A.prof) {                                         \
+    if (A.prof && grp == 0) {                             \
       long long now_ = clock64();                         \
       pf[slot] += now_ - tmark;                           \
       tmark = now_;                                       \
@@ -380,7 +420,7 @@ __global__ void __launch_bounds__(MapTraits<U, UW>::NW * 32, 1) wavernn_grid_ker
     float* h2n = A.h2 + (cur ^ 1) * RB;
 
     // ================= P0: read back the previous step's winner, then the I layer =================
-    for (int tb = 0; tb < Bp; tb += BT) {
+    for (int tb = tb_lo; tb < tb_hi; tb += BT) {
       for (int ul = tid; ul < BT; ul += NT) {
         const int u = tb + ul;
         float x = 0.f;
@@ -399,41 +439,41 @@ __global__ void __launch_bounds__(MapTraits<U, UW>::NW * 32, 1) wavernn_grid_ker
         g.W = Wb + M.oI_w; g.ldw = M.ldC; g.nseg = 2;
         g.seg[0] = Seg{melT, M.FEAT / 4};
         g.seg[1] = Seg{auxT, AUX / 4};
-        wide_partials<NW, U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
+        wide_partials<NWG, U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
       } else {
         stage_rows<NT>(stA, melT, M.FEAT * G, tid);
         stage_rows<NT>(stA + M.FEAT * G, auxT, AUX * G, tid);
-        __syncthreads();
-        narrow_rows<G, 1>(nout, 0, Wb + M.oI_w, M.ldC, stA, M.ldC / 4, kUPC, 0, NW, warp, lane);
+        group_sync<GROUPS, NT>(grp);
+        narrow_rows<G, 1>(nout, 0, Wb + M.oI_w, M.ldC, stA, M.ldC / 4, kUPC, 0, NWG, warp, lane);
       }
-      __syncthreads();
+      group_sync<GROUPS, NT>(grp);
       for (int idx = tid; idx < BT * kUPC; idx += NT) {
         const int ul = idx % BT, j = idx / BT;
         float v = part_sum<KS1, kUPC, BT>(res, 0, j, ul);
         v = fmaf(wIx[j], xs[ul], v) + bI[j];
         A.Iout[(size_t)(c * kUPC + j) * Bp + tb + ul] = v;
       }
-      if (tb + BT < Bp) __syncthreads();
+      if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(0);
-    if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
     PROF_MARK(1);
 
     // ================= P1: GRU 1 =================
-    for (int tb = 0; tb < Bp; tb += BT) {
+    for (int tb = tb_lo; tb < tb_hi; tb += BT) {
       if constexpr (MT::kWide) {
         Gemm gi{}, gh{};
         gi.W = Wb + M.oih1; gi.ldw = R; gi.nseg = 1; gi.seg[0] = Seg{A.Iout, R / 4};
         gh.W = Wb + M.ohh1; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h1c, R / 4};
-        wide_partials<NW, U, UW, 3 * kUPC, 2>(part, gi, gh, tb, Bp, warp, lane);
+        wide_partials<NWG, U, UW, 3 * kUPC, 2>(part, gi, gh, tb, Bp, warp, lane);
       } else {
         stage_rows<NT>(stA, A.Iout, R * G, tid);
         stage_rows<NT>(stB, h1c, R * G, tid);
-        __syncthreads();
-        narrow_rows<G, 3>(nout, 0, Wb + M.oih1, R, stA, R / 4, 3 * kUPC, 0, NW / 2, warp, lane);
-        narrow_rows<G, 3>(nout, 1, Wb + M.ohh1, R, stB, R / 4, 3 * kUPC, NW / 2, NW / 2, warp, lane);
+        group_sync<GROUPS, NT>(grp);
+        narrow_rows<G, 3>(nout, 0, Wb + M.oih1, R, stA, R / 4, 3 * kUPC, 0, NWG / 2, warp, lane);
+        narrow_rows<G, 3>(nout, 1, Wb + M.ohh1, R, stB, R / 4, 3 * kUPC, NWG / 2, NWG / 2, warp, lane);
       }
-      __syncthreads();
+      group_sync<GROUPS, NT>(grp);
       const float* bih = Wb + M.obih1; const float* bhh = Wb + M.obhh1;
       for (int idx = tid; idx < BT * kUPC; idx += NT) {
         const int ul = idx % BT, j = idx / BT;
@@ -450,29 +490,29 @@ __global__ void __launch_bounds__(MapTraits<U, UW>::NW * 32, 1) wavernn_grid_ker
         h1n[o] = h;
         A.x1[o] = resid + h;
       }
-      if (tb + BT < Bp) __syncthreads();
+      if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(2);
-    if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
     PROF_MARK(3);
 
     // ================= P2: GRU 2 =================
-    for (int tb = 0; tb < Bp; tb += BT) {
+    for (int tb = tb_lo; tb < tb_hi; tb += BT) {
       if constexpr (MT::kWide) {
         Gemm gi{}, gh{};
         gi.W = Wb + M.oih2; gi.ldw = M.ldX; gi.nseg = 2; gi.seg[0] = Seg{A.x1, R / 4};
         gi.seg[1] = Seg{auxT + (size_t)AUX * Bp, AUX / 4};
         gh.W = Wb + M.ohh2; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h2c, R / 4};
-        wide_partials<NW, U, UW, 3 * kUPC, 2>(part, gi, gh, tb, Bp, warp, lane);
+        wide_partials<NWG, U, UW, 3 * kUPC, 2>(part, gi, gh, tb, Bp, warp, lane);
       } else {
         stage_rows<NT>(stA, A.x1, R * G, tid);
         stage_rows<NT>(stA + R * G, auxT + (size_t)AUX * Bp, AUX * G, tid);
         stage_rows<NT>(stB, h2c, R * G, tid);
-        __syncthreads();
-        narrow_rows<G, 3>(nout, 0, Wb + M.oih2, M.ldX, stA, M.ldX / 4, 3 * kUPC, 0, NW / 2, warp, lane);
-        narrow_rows<G, 3>(nout, 1, Wb + M.ohh2, R, stB, R / 4, 3 * kUPC, NW / 2, NW / 2, warp, lane);
+        group_sync<GROUPS, NT>(grp);
+        narrow_rows<G, 3>(nout, 0, Wb + M.oih2, M.ldX, stA, M.ldX / 4, 3 * kUPC, 0, NWG / 2, warp, lane);
+        narrow_rows<G, 3>(nout, 1, Wb + M.ohh2, R, stB, R / 4, 3 * kUPC, NWG / 2, NWG / 2, warp, lane);
       }
-      __syncthreads();
+      group_sync<GROUPS, NT>(grp);
       const float* bih = Wb + M.obih2; const float* bhh = Wb + M.obhh2;
       for (int idx = tid; idx < BT * kUPC; idx += NT) {
         const int ul = idx % BT, j = idx / BT;
@@ -489,76 +529,76 @@ __global__ void __launch_bounds__(MapTraits<U, UW>::NW * 32, 1) wavernn_grid_ker
         h2n[o] = h;
         A.x2[o] = resid + h;
       }
-      if (tb + BT < Bp) __syncthreads();
+      if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(4);
-    if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
     PROF_MARK(5);
 
     // ================= P3: fc1 + relu  (CTA 0 also recycles the argmax slot the NEXT step will use) =================
     if (c == 0)
-      for (int u = tid; u < Bp; u += NT) A.best[(size_t)((t + 1) & 1) * Bp + u] = 0ull;
-    for (int tb = 0; tb < Bp; tb += BT) {
+      for (int u = tb_lo + tid; u < tb_hi; u += NT) A.best[(size_t)((t + 1) & 1) * Bp + u] = 0ull;
+    for (int tb = tb_lo; tb < tb_hi; tb += BT) {
       if constexpr (MT::kWide) {
         Gemm g{};
         g.W = Wb + M.ofc1; g.ldw = M.ldX; g.nseg = 2; g.seg[0] = Seg{A.x2, R / 4};
         g.seg[1] = Seg{auxT + (size_t)2 * AUX * Bp, AUX / 4};
-        wide_partials<NW, U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
+        wide_partials<NWG, U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
       } else {
         stage_rows<NT>(stA, A.x2, R * G, tid);
         stage_rows<NT>(stA + R * G, auxT + (size_t)2 * AUX * Bp, AUX * G, tid);
-        __syncthreads();
-        narrow_rows<G, 1>(nout, 0, Wb + M.ofc1, M.ldX, stA, M.ldX / 4, kUPC, 0, NW, warp, lane);
+        group_sync<GROUPS, NT>(grp);
+        narrow_rows<G, 1>(nout, 0, Wb + M.ofc1, M.ldX, stA, M.ldX / 4, kUPC, 0, NWG, warp, lane);
       }
-      __syncthreads();
+      group_sync<GROUPS, NT>(grp);
       const float* b = Wb + M.obfc1;
       for (int idx = tid; idx < BT * kUPC; idx += NT) {
         const int ul = idx % BT, j = idx / BT;
         A.f1[(size_t)(c * kUPC + j) * Bp + tb + ul] = fmaxf(part_sum<KS1, kUPC, BT>(res, 0, j, ul) + b[j], 0.f);
       }
-      if (tb + BT < Bp) __syncthreads();
+      if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(6);
-    if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
     PROF_MARK(7);
 
     // ================= P4: fc2 + relu =================
-    for (int tb = 0; tb < Bp; tb += BT) {
+    for (int tb = tb_lo; tb < tb_hi; tb += BT) {
       if constexpr (MT::kWide) {
         Gemm g{};
         g.W = Wb + M.ofc2; g.ldw = M.ldF; g.nseg = 2; g.seg[0] = Seg{A.f1, F / 4};
         g.seg[1] = Seg{auxT + (size_t)3 * AUX * Bp, AUX / 4};
-        wide_partials<NW, U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
+        wide_partials<NWG, U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
       } else {
         stage_rows<NT>(stA, A.f1, F * G, tid);
         stage_rows<NT>(stA + F * G, auxT + (size_t)3 * AUX * Bp, AUX * G, tid);
-        __syncthreads();
-        narrow_rows<G, 1>(nout, 0, Wb + M.ofc2, M.ldF, stA, M.ldF / 4, kUPC, 0, NW, warp, lane);
+        group_sync<GROUPS, NT>(grp);
+        narrow_rows<G, 1>(nout, 0, Wb + M.ofc2, M.ldF, stA, M.ldF / 4, kUPC, 0, NWG, warp, lane);
       }
-      __syncthreads();
+      group_sync<GROUPS, NT>(grp);
       const float* b = Wb + M.obfc2;
       for (int idx = tid; idx < BT * kUPC; idx += NT) {
         const int ul = idx % BT, j = idx / BT;
         A.f2[(size_t)(c * kUPC + j) * Bp + tb + ul] = fmaxf(part_sum<KS1, kUPC, BT>(res, 0, j, ul) + b[j], 0.f);
       }
-      if (tb + BT < Bp) __syncthreads();
+      if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(8);
-    if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
     PROF_MARK(9);
 
     // ================= P5: fc3 + distributed Gumbel-max sampling =================
-    for (int tb = 0; tb < Bp; tb += BT) {
+    for (int tb = tb_lo; tb < tb_hi; tb += BT) {
       if constexpr (MT::kWide) {
         Gemm g{};
         g.W = Wb + M.ofc3; g.ldw = F; g.nseg = 1; g.seg[0] = Seg{A.f2, F / 4};
-        wide_partials<NW, U, UW, kCPC, 1>(part, g, g, tb, Bp, warp, lane);
+        wide_partials<NWG, U, UW, kCPC, 1>(part, g, g, tb, Bp, warp, lane);
       } else {
         stage_rows<NT>(stA, A.f2, F * G, tid);
-        __syncthreads();
-        narrow_rows<G, 1>(nout, 0, Wb + M.ofc3, F, stA, F / 4, kCPC, 0, NW, warp, lane);
+        group_sync<GROUPS, NT>(grp);
+        narrow_rows<G, 1>(nout, 0, Wb + M.ofc3, F, stA, F / 4, kCPC, 0, NWG, warp, lane);
       }
-      __syncthreads();
+      group_sync<GROUPS, NT>(grp);
       const float* b = Wb + M.obfc3;
       for (int ul = tid; ul < BT; ul += NT) {
         const int u = tb + ul;
@@ -586,19 +626,19 @@ __global__ void __launch_bounds__(MapTraits<U, UW>::NW * 32, 1) wavernn_grid_ker
           atomicMax(A.best + (size_t)(t & 1) * Bp + u, bestp);
         }
       }
-      if (tb + BT < Bp) __syncthreads();
+      if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(10);
-    if (!grid_barrier(A.barrier, (++nbar) * ncta, A.error)) return;
+    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
     PROF_MARK(11);
   }
-  if (A.prof && tid == 0)
+  if (A.prof && grp == 0 && tid == 0)
     for (int i = 0; i < 12; ++i) A.prof[(size_t)c * 12 + i] = pf[i];
 #undef PROF_MARK
   // the last step's winner
   if (c == 0 && A.steps > 0) {
     const int t = A.steps;
-    for (int u = tid; u < A.B; u += NT) {
+    for (int u = tb_lo + tid; u < tb_hi && u < A.B; u += NT) {
       unsigned long long pk = __ldcg(A.best + (size_t)((t - 1) & 1) * Bp + u);
       A.labels[(size_t)u * A.S + (t - 1)] = (int16_t)unpack_idx(pk);
     }
