@@ -134,6 +134,50 @@ int64_t b200tts_wavernn_launch_count(const b200tts_wavernn* ctx);
  * generate call; blocks until that kernel has finished.  Negative on error. */
 double b200tts_wavernn_last_kernel_ms(b200tts_wavernn* ctx);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tacotron-2 forward-attention decoder loop (secondary hot path).
+ *   b200tts_taco_create  <- the decoder-side variables tf.train.Saver restores (tacotron_synthesize.py:76-78), by their
+ *                           checkpoint names minus the "Tacotron_model/inference/" prefix
+ *   b200tts_taco_decode  <- dynamic_decode(CustomDecoder(TacotronDecoderCell, TacoTestHelper)) tacotron/models/tacotron.py:99-103
+ *                           = Architecture_wrappers.py:175-218 + attention.py:119-231 + modules.py:114-142,240-251,304,334-342
+ *                           + custom_decoder.py:105-135 + helpers.py:36-66
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t num_mels;         /* 80   tacotron_hparams.py num_mels                */
+  int32_t prenet_units;     /* 256  prenet_layers = [256, 256]                  */
+  int32_t lstm_units;       /* 256  decoder_lstm_units (checkpoint kernels are [768+256,1024] and [512,1024]) */
+  int32_t enc_dim;          /* 512  2 * encoder_lstm_units                      */
+  int32_t attn_dim;         /* 128  attention_dim                               */
+  int32_t attn_filters;     /* 32   attention_filters                           */
+  int32_t attn_kernel;      /* 31   attention_kernel                            */
+  float zoneout;            /* 0.1  tacotron_zoneout_rate                       */
+} b200tts_taco_cfg;
+
+enum { B200TTS_TACO_DROPOUT_PHILOX = 0, B200TTS_TACO_DROPOUT_EXT = 1 };
+typedef struct {
+  int32_t mode;
+  uint64_t seed;
+  uint64_t utterance_offset;
+  const uint8_t* d_masks;   /* EXT: keep flags [B][max_steps][2][prenet_units]; prenet dropout is ON at inference (modules.py:249) */
+} b200tts_taco_dropout;
+
+typedef struct b200tts_taco b200tts_taco;
+
+int b200tts_taco_create(b200tts_taco** out, int device, const b200tts_taco_cfg* cfg, const b200tts_tensor* weights, int n_weights);
+void b200tts_taco_destroy(b200tts_taco* ctx);
+
+/* d_memory [B][Tx_max][enc_dim] encoder outputs, d_lengths [B] (<= Tx_max <= 512).  Every sentence runs until its own
+ * stop token exceeds 0.5 or max_steps.  window != 0 enables the inference attention window of forward_attention.py:171-215.
+ * Outputs: d_frames [B][max_steps][num_mels] raw decoder outputs (before the clip of tacotron.py:111), d_stop [B][max_steps],
+ * d_align [B][max_steps][Tx_max] (may be NULL), d_nsteps [B] = frames produced (the last one is the frame whose stop fired). */
+int b200tts_taco_decode(b200tts_taco* ctx, const float* d_memory, const int32_t* d_lengths, int B, int Tx_max,
+                        const b200tts_taco_dropout* dropout, int max_steps, int window, float* d_frames, float* d_stop,
+                        float* d_align, int32_t* d_nsteps, void* stream);
+
+/* The keep flags the PHILOX dropout mode draws: d_masks [B][steps][2][prenet_units]. */
+int b200tts_taco_philox_masks(int device, uint64_t seed, uint64_t utterance_offset, int B, int steps, int prenet_units,
+                              uint8_t* d_masks, void* stream);
+
 /* Debug aid: mean SM cycles per CTA spent in {compute, barrier} of each of the 6 phases of the last grid-kernel
  * launch; only recorded when the environment variable B200TTS_GRID_PROF is set while generating. */
 int b200tts_wavernn_debug_phase_cycles(b200tts_wavernn* ctx, double* out12);

@@ -1,0 +1,208 @@
+"""CPU oracle for the Tacotron-2 forward-attention inference path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+*** PARITY UNPINNED ***  The reference runs on TensorFlow 1.14 (`tf.contrib.*`), which is not installable here and
+the reference ships no tests / golden mels for this path.  This is therefore a numpy (float32)
+restatement written from the reference's source plus the documented semantics of the TF 1.14 ops it calls
+(`tf.nn.rnn_cell.LSTMCell`: gates i,j,f,o, forget_bias 1.0, kernel [in+units, 4*units]; `tf.layers.batch_normalization`
+epsilon 1e-3 with moving statistics; `tf.layers.conv1d` 'same' cross-correlation with kernel [k,in,out];
+`tf.layers.dropout` keep-scaling; `BahdanauAttention` bias-free memory/query layers, -inf score masking, softmax).
+Weak pins that ARE checked (tests/test_tacotron_oracle.py): variable names/shapes of the shipped checkpoint, and that on a
+real training sentence (train.txt line 241, 444 ground-truth frames) the decoder attends monotonically and its stop token
+fires near the ground-truth length.
+
+Only tests/, __graft_entry__.smoke() and bench.py may import this module.  Reference citations are relative to the
+reference root.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+P = 'decoder/'
+
+
+def _sigmoid(x):
+    return (F32(1) / (F32(1) + np.exp(-x, dtype=F32))).astype(F32)
+
+
+def lstm_cell(x, c, h, kernel, bias, forget_bias=1.0):
+    """tf.nn.rnn_cell.LSTMCell step (used at tacotron/models/modules.py:100,118): returns (new_c, new_h)."""
+    z = (np.concatenate([x, h], axis=-1) @ kernel + bias).astype(F32)
+    i, j, f, o = np.split(z, 4, axis=-1)
+    new_c = (_sigmoid(f + F32(forget_bias)) * c + _sigmoid(i) * np.tanh(j, dtype=F32)).astype(F32)
+    new_h = (_sigmoid(o) * np.tanh(new_c, dtype=F32)).astype(F32)
+    return new_c, new_h
+
+
+def zoneout_lstm(x, c, h, kernel, bias, zoneout=0.1):
+    """ZoneoutLSTMCell.__call__ at inference, modules.py:114-142: the OUTPUT is the un-zoned new_h (:118,:142), the
+    carried state is (1-z)*new + z*prev (:137-138)."""
+    new_c, new_h = lstm_cell(x, c, h, kernel, bias)
+    zc = ((F32(1) - F32(zoneout)) * new_c + F32(zoneout) * c).astype(F32)
+    zh = ((F32(1) - F32(zoneout)) * new_h + F32(zoneout) * h).astype(F32)
+    return new_h, zc, zh
+
+
+def conv1d_same(x, kernel, bias):
+    """tf.layers.conv1d(padding='same') on [T, Cin] with kernel [k, Cin, Cout] (modules.py:382-387)."""
+    k = kernel.shape[0]
+    T = x.shape[0]
+    left = (k - 1) // 2
+    xp = np.zeros((T + k - 1, x.shape[1]), dtype=F32)
+    xp[left:left + T] = x
+    y = np.zeros((T, kernel.shape[2]), dtype=F32)
+    for j in range(k):
+        y += (xp[j:j + T] @ kernel[j]).astype(F32)
+    return (y + bias).astype(F32)
+
+
+def batch_norm(x, w, prefix, eps=1e-3):
+    """tf.layers.batch_normalization(training=False): moving statistics, epsilon 1e-3 (modules.py:388)."""
+    g, b = w[prefix + '/gamma'], w[prefix + '/beta']
+    m, v = w[prefix + '/moving_mean'], w[prefix + '/moving_variance']
+    return ((x - m) * (g / np.sqrt(v + F32(eps))) + b).astype(F32)
+
+
+def conv_block(x, w, scope, activation):
+    """modules.py:379-391 with batch_norm_position='after' (tacotron_hparams.py:127): conv -> activation -> BN; dropout off."""
+    y = conv1d_same(x, w[scope + '/conv1d/kernel'], w[scope + '/conv1d/bias'])
+    y = activation(y)
+    return batch_norm(y, w, scope + '/batch_normalization')
+
+
+def encoder(w, ids):
+    """Embedding lookup (tacotron.py:44-47) -> 3 x conv k5/256 ReLU -> BN (modules.py:168-174) -> BiLSTM 2x256 with zoneout
+    (modules.py:207-217).  ids: int [Tx].  Returns memory [Tx, 512]."""
+    x = w['inputs_embedding'][np.asarray(ids)].astype(F32)
+    for i in (1, 2, 3):
+        x = conv_block(x, w, f'encoder_convolutions/conv_layer_{i}_encoder_convolutions', lambda v: np.maximum(v, F32(0)))
+    Tx = x.shape[0]
+    outs = []
+    for direction, order in (('fw', range(Tx)), ('bw', range(Tx - 1, -1, -1))):
+        k = w[f'encoder_LSTM/bidirectional_rnn/{direction}/encoder_{direction}_LSTM/kernel']
+        b = w[f'encoder_LSTM/bidirectional_rnn/{direction}/encoder_{direction}_LSTM/bias']
+        U = k.shape[1] // 4
+        c = np.zeros((1, U), dtype=F32)
+        h = np.zeros((1, U), dtype=F32)
+        o = np.zeros((Tx, U), dtype=F32)
+        for t in order:
+            out, c, h = zoneout_lstm(x[t:t + 1], c, h, k, b)
+            o[t] = out[0]
+        outs.append(o)
+    return np.concatenate(outs, axis=1).astype(F32)
+
+
+def location_features(w, cum):
+    """location_convolution (attention.py:100-102) + location_layer (:104-105) on cumulated alignments [Tx]."""
+    K = w[P + 'Location_Sensitive_Attention/location_features_convolution/kernel']          # [31, 1, 32]
+    f = conv1d_same(cum[:, None].astype(F32), K, w[P + 'Location_Sensitive_Attention/location_features_convolution/bias'])
+    return (f @ w[P + 'Location_Sensitive_Attention/location_features_layer/kernel']).astype(F32)   # [Tx, 128]
+
+
+def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, zoneout=0.1):
+    """The decoder while-loop for ONE sentence: dynamic_decode(CustomDecoder(TacotronDecoderCell, TacoTestHelper))
+    (tacotron.py:99-103; custom_decoder.py:105-135; helpers.py:36-66; Architecture_wrappers.py:175-218;
+    attention.py:119-231; `window=True` adds forward_attention.py:171-215).
+
+    memory [Tx, 512]; dropout_masks optional [steps, 2, 256] of {0,1} keep flags for the two prenet layers
+    (drawn from RandomState(seed) when None; prenet dropout is ON at inference, modules.py:249).
+    Returns dict(frames [n,80] raw decoder outputs, stop [n], alignments [n,Tx], n_steps, masks).
+    """
+    Tx = memory.shape[0]
+    keys = (memory @ w['memory_layer/kernel']).astype(F32)                                   # BahdanauAttention ctor
+    Wq = w[P + 'Location_Sensitive_Attention/query_layer/kernel']
+    v_a = w[P + 'Location_Sensitive_Attention/attention_variable_projection']
+    b_a = w[P + 'Location_Sensitive_Attention/attention_bias']
+    k1 = w[P + 'decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/kernel']
+    b1 = w[P + 'decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/bias']
+    k2 = w[P + 'decoder_LSTM/multi_rnn_cell/cell_1/decoder_LSTM_2/kernel']
+    b2 = w[P + 'decoder_LSTM/multi_rnn_cell/cell_1/decoder_LSTM_2/bias']
+    U = k1.shape[1] // 4
+    rs = np.random.RandomState(seed)
+    c1 = h1 = c2 = h2 = np.zeros((1, U), dtype=F32)
+    ctx = np.zeros((1, memory.shape[1]), dtype=F32)                                          # zero_state attention (:164)
+    alpha = np.zeros(Tx, dtype=F32); alpha[0] = 1                                            # init_alpha (attention.py:112)
+    cum = alpha.copy()                                                                       # init_cumulated_alignments
+    mu = F32(0.5)                                                                            # init_mu
+    max_att, pos_rec = 0, 0
+    x = np.zeros((1, 80), dtype=F32)                                                         # _go_frames (helpers.py:149)
+    frames, stops, aligns, masks = [], [], [], []
+    for step in range(max_iters):
+        # -- prenet, dropout always on (modules.py:240-251)
+        m = dropout_masks[step] if dropout_masks is not None else (rs.uniform(size=(2, 256)) >= 0.5)
+        m = np.asarray(m, dtype=F32)
+        masks.append(m)
+        p = x
+        for li in (1, 2):
+            p = np.maximum((p @ w[P + f'decoder_prenet/dense_{li}/kernel'] + w[P + f'decoder_prenet/dense_{li}/bias']).astype(F32), 0)
+            p = (p * m[li - 1] * F32(2.0)).astype(F32)                                       # keep-prob 0.5 scaling
+        # -- 2 x zoneout LSTM (Architecture_wrappers.py:180-183)
+        o1, c1, h1 = zoneout_lstm(np.concatenate([p, ctx], axis=1), c1, h1, k1, b1, zoneout)
+        o2, c2, h2 = zoneout_lstm(o1, c2, h2, k2, b2, zoneout)
+        # -- attention (attention.py:132-167)
+        q = (o2 @ Wq).astype(F32)                                                            # [1,128]
+        loc = location_features(w, cum)
+        energy = (np.tanh(keys + q + loc + b_a, dtype=F32) * v_a).sum(axis=1).astype(F32)    # [Tx]
+        e = np.exp(energy - energy.max(), dtype=F32)
+        a = (e / e.sum(dtype=F32)).astype(F32)                                               # softmax (probability_fn)
+        cum = (cum + a).astype(F32)                                                          # :154 (pre-modulation)
+        shift = np.concatenate([[F32(0)], alpha[:-1]]).astype(F32)
+        al = (((F32(1) - mu) * alpha + mu * shift + F32(1e-10)) * a).astype(F32)             # :167
+        new_max = int(np.argmax(al))
+        if window:                                                                           # forward_attention.py:171-215
+            new_max = max_att if new_max <= max_att else max_att + 1
+            if pos_rec < 5 and 2 < new_max:
+                new_max = max_att
+            if new_max == max_att:
+                pos_rec = pos_rec + 1
+            else:
+                pos_rec = 1
+            if not pos_rec < 9:
+                new_max, pos_rec = new_max + 1, 1
+            idx = np.arange(Tx)
+            keep = (idx >= new_max - 2) & (idx < new_max + 3)
+            al = np.where(keep, al, F32(0)).astype(F32)
+            peak = idx == min(max(new_max, 0), Tx - 1)
+            al = np.where(peak & (idx < new_max + 1), F32(0.1) + al.sum(dtype=F32) * F32(2.0), al).astype(F32)
+        max_att = new_max
+        al = (al / al.sum(dtype=F32)).astype(F32)                                            # :220
+        ctx = (al[None, :] @ memory).astype(F32)                                             # :222
+        mu = _sigmoid((np.concatenate([ctx, o2], axis=1) @ w[P + 'dense/kernel'] + w[P + 'dense/bias']).astype(F32))[0, 0]
+        alpha = al
+        # -- projections (Architecture_wrappers.py:196-199)
+        pin = np.concatenate([o2, ctx], axis=1)
+        frame = (pin @ w[P + 'linear_transform_projection/projection_linear_transform_projection/kernel']
+                 + w[P + 'linear_transform_projection/projection_linear_transform_projection/bias']).astype(F32)
+        stop = _sigmoid((pin @ w[P + 'stop_token_projection/projection_stop_token_projection/kernel']
+                         + w[P + 'stop_token_projection/projection_stop_token_projection/bias']).astype(F32))[0, 0]
+        frames.append(frame[0]); stops.append(stop); aligns.append(al)
+        x = frame                                                                            # helpers.py:64 (r = 1)
+        if stop > 0.5:                                                                       # tf.round, half-to-even (:45)
+            break
+    return dict(frames=np.stack(frames), stop=np.array(stops, dtype=F32), alignments=np.stack(aligns),
+                n_steps=len(frames), masks=np.stack(masks))
+
+
+def postnet(w, dec):
+    """Clip (tacotron.py:111-112) -> 5 x conv k5 (tanh x4, linear) -> BN (modules.py:368-376) -> projection -> residual add
+    -> clip (tacotron.py:115-129).  dec [n,80] -> mel [n,80]."""
+    lo, hi = F32(-4.0 - 0.1), F32(4.0)
+    d = np.clip(dec, lo, hi).astype(F32)
+    x = d
+    for i in (1, 2, 3, 4):
+        x = conv_block(x, w, f'postnet_convolutions/conv_layer_{i}_postnet_convolutions', lambda v: np.tanh(v, dtype=F32))
+    x = conv_block(x, w, 'postnet_convolutions/conv_layer_5_postnet_convolutions', lambda v: v)
+    r = (x @ w['postnet_projection/projection_postnet_projection/kernel']
+         + w['postnet_projection/projection_postnet_projection/bias']).astype(F32)
+    return np.clip(d + r, lo, hi).astype(F32)
+
+
+def synthesize(w, ids, **kw):
+    """Synthesizer.synthesize numerics (tacotron_synthesize.py:97-116): returns (mel_for_wavernn [n,80] in [0,1], dict)."""
+    mem = encoder(w, ids)
+    d = decode(w, mem, **kw)
+    mel = postnet(w, d['frames'])
+    rounded = np.round(d['stop'])
+    target = int(np.argmax(rounded == 1)) if (rounded == 1).any() else len(rounded)          # :104-105
+    mel = np.clip(mel[:target], -4.0, 4.0)                                                   # :107-108
+    return np.clip((mel + 4.0) / 8.0, 0, 1).astype(F32), dict(decode=d, memory=mem, target_length=target)   # :115

@@ -45,6 +45,15 @@ class GenOpts(C.Structure):
                 ('max_steps', C.c_int32)]
 
 
+class TacoCfg(C.Structure):
+    _fields_ = [('num_mels', C.c_int32), ('prenet_units', C.c_int32), ('lstm_units', C.c_int32), ('enc_dim', C.c_int32),
+                ('attn_dim', C.c_int32), ('attn_filters', C.c_int32), ('attn_kernel', C.c_int32), ('zoneout', C.c_float)]
+
+
+class TacoDropout(C.Structure):
+    _fields_ = [('mode', C.c_int32), ('seed', C.c_uint64), ('utterance_offset', C.c_uint64), ('d_masks', C.c_void_p)]
+
+
 # every symbol include/b200tts.h declares: (restype, argtypes)
 SIGNATURES = {
     'b200tts_abi_version': (C.c_int, []),
@@ -63,6 +72,11 @@ SIGNATURES = {
     'b200tts_wavernn_launch_count': (C.c_int64, [C.c_void_p]),
     'b200tts_wavernn_last_kernel_ms': (C.c_double, [C.c_void_p]),
     'b200tts_wavernn_debug_phase_cycles': (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    'b200tts_taco_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(TacoCfg), C.POINTER(Tensor), C.c_int]),
+    'b200tts_taco_destroy': (None, [C.c_void_p]),
+    'b200tts_taco_decode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(TacoDropout), C.c_int,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'b200tts_taco_philox_masks': (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -14,6 +14,7 @@
 #include "wavernn_upsample.cuh"
 #include "wavernn_utt.cuh"
 #include "wavernn_grid.cuh"
+#include "taco_decoder.cuh"
 
 using namespace b200tts;
 
@@ -758,6 +759,134 @@ extern "C" int b200tts_philox_exponential(int device, uint64_t seed, uint64_t ut
   size_t total = (size_t)n_steps * B * (n_classes / 4);
   unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
   philox_dump_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, utterance_offset, B, step0, n_steps, n_classes, d_q);
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+// ================================================================================================================
+// Tacotron-2 decoder
+// ================================================================================================================
+struct b200tts_taco {
+  int device = 0;
+  b200tts_taco_cfg cfg{};
+  DeviceBuf weights, keys;
+  TacoWeights tw{};
+  int64_t launches = 0;
+};
+
+extern "C" int b200tts_taco_create(b200tts_taco** out, int device, const b200tts_taco_cfg* cfg, const b200tts_tensor* weights,
+                                   int n_weights) {
+  API_BEGIN
+  REQUIRE(out && cfg && weights && n_weights > 0, B200TTS_EINVAL, "null argument");
+  *out = nullptr;
+  const b200tts_taco_cfg& c = *cfg;
+  const int M = c.num_mels, P = c.prenet_units, U = c.lstm_units, E = c.enc_dim, AD = c.attn_dim, NF = c.attn_filters, KW = c.attn_kernel;
+  REQUIRE(M % 4 == 0 && P % 4 == 0 && U % 4 == 0 && E % 4 == 0 && AD % 4 == 0, B200TTS_EINVAL, "dims must be multiples of 4");
+  REQUIRE(M <= 96 && P == 256 && 4 * U == 1024 && E <= 1024 && AD <= 256 && KW % 2 == 1 && KW * NF <= 992 && NF * AD <= 4096,
+          B200TTS_EINVAL, "decoder dims outside what taco_decoder_kernel is laid out for");
+  int ndev = 0;
+  B200_CUDA(cudaGetDeviceCount(&ndev));
+  REQUIRE(device >= 0 && device < ndev, B200TTS_EINVAL, "no such CUDA device");
+  DeviceGuard dg(device);
+  TensorMap tm;
+  for (int i = 0; i < n_weights; ++i)
+    if (weights[i].name) tm[weights[i].name] = &weights[i];
+  auto ctx = new b200tts_taco();
+  struct Cleanup { b200tts_taco* c; ~Cleanup() { if (c) b200tts_taco_destroy(c); } } cleanup{ctx};
+  ctx->device = device;
+  ctx->cfg = c;
+  Packer pk;
+  auto copy = [&](const std::string& name, std::initializer_list<int64_t> shape) {
+    const b200tts_tensor* t = need(tm, name, shape);
+    size_t n = 1;
+    for (int64_t s : shape) n *= (size_t)s;
+    size_t off = pk.add(n);
+    std::memcpy(&pk.h[off], t->data, n * sizeof(float));
+    return off;
+  };
+  const std::string D = "decoder/", L = D + "Location_Sensitive_Attention/";
+  size_t o[21];
+  o[0] = copy(D + "decoder_prenet/dense_1/kernel", {M, P}); o[1] = copy(D + "decoder_prenet/dense_1/bias", {P});
+  o[2] = copy(D + "decoder_prenet/dense_2/kernel", {P, P}); o[3] = copy(D + "decoder_prenet/dense_2/bias", {P});
+  o[4] = copy(D + "decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/kernel", {P + E + U, 4 * U});
+  o[5] = copy(D + "decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/bias", {4 * U});
+  o[6] = copy(D + "decoder_LSTM/multi_rnn_cell/cell_1/decoder_LSTM_2/kernel", {2 * U, 4 * U});
+  o[7] = copy(D + "decoder_LSTM/multi_rnn_cell/cell_1/decoder_LSTM_2/bias", {4 * U});
+  o[8] = copy(L + "query_layer/kernel", {U, AD});
+  o[9] = copy(L + "location_features_convolution/kernel", {KW, 1, NF}); o[10] = copy(L + "location_features_convolution/bias", {NF});
+  o[11] = copy(L + "location_features_layer/kernel", {NF, AD});
+  o[12] = copy(L + "attention_variable_projection", {AD}); o[13] = copy(L + "attention_bias", {AD});
+  o[14] = copy(D + "dense/kernel", {E + U, 1}); o[15] = copy(D + "dense/bias", {1});
+  o[16] = copy(D + "linear_transform_projection/projection_linear_transform_projection/kernel", {U + E, M});
+  o[17] = copy(D + "linear_transform_projection/projection_linear_transform_projection/bias", {M});
+  o[18] = copy(D + "stop_token_projection/projection_stop_token_projection/kernel", {U + E, 1});
+  o[19] = copy(D + "stop_token_projection/projection_stop_token_projection/bias", {1});
+  o[20] = copy("memory_layer/kernel", {E, AD});
+  ctx->weights.ensure(pk.h.size() * sizeof(float));
+  B200_CUDA(cudaMemcpy(ctx->weights.p, pk.h.data(), pk.h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  const float* b = ctx->weights.as<float>();
+  TacoWeights& w = ctx->tw;
+  w.pre1_k = b + o[0]; w.pre1_b = b + o[1]; w.pre2_k = b + o[2]; w.pre2_b = b + o[3];
+  w.l1_k = b + o[4]; w.l1_b = b + o[5]; w.l2_k = b + o[6]; w.l2_b = b + o[7];
+  w.q_k = b + o[8]; w.loc_k = b + o[9]; w.loc_b = b + o[10]; w.locl_k = b + o[11]; w.v_a = b + o[12]; w.b_a = b + o[13];
+  w.mu_k = b + o[14]; w.mu_b = b + o[15]; w.fr_k = b + o[16]; w.fr_b = b + o[17]; w.st_k = b + o[18]; w.st_b = b + o[19];
+  w.mem_k = b + o[20];
+  w.mels = M; w.P = P; w.U = U; w.E = E; w.A = AD; w.NF = NF; w.KW = KW; w.zoneout = c.zoneout;
+  cleanup.c = nullptr;
+  *out = ctx;
+  API_END
+}
+
+extern "C" void b200tts_taco_destroy(b200tts_taco* ctx) {
+  if (!ctx) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(ctx->device);
+  ctx->weights.release();
+  ctx->keys.release();
+  if (prev >= 0) cudaSetDevice(prev);
+  delete ctx;
+}
+
+extern "C" int b200tts_taco_decode(b200tts_taco* ctx, const float* d_memory, const int32_t* d_lengths, int B, int Tx_max,
+                                   const b200tts_taco_dropout* dropout, int max_steps, int window, float* d_frames, float* d_stop,
+                                   float* d_align, int32_t* d_nsteps, void* stream) {
+  API_BEGIN
+  REQUIRE(ctx && d_memory && d_lengths && d_frames && d_stop && d_nsteps, B200TTS_EINVAL, "null argument");
+  REQUIRE(B >= 1 && Tx_max >= 1 && Tx_max <= kTacoMaxTx && max_steps >= 1, B200TTS_EINVAL, "B, Tx_max (<= 512), max_steps out of range");
+  b200tts_taco_dropout d{};
+  if (dropout) d = *dropout;
+  REQUIRE(d.mode == B200TTS_TACO_DROPOUT_PHILOX || (d.mode == B200TTS_TACO_DROPOUT_EXT && d.d_masks), B200TTS_EINVAL,
+          "bad dropout descriptor");
+  DeviceGuard dg(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const TacoWeights& w = ctx->tw;
+  ctx->keys.ensure((size_t)B * Tx_max * w.A * sizeof(float));
+  taco_keys_kernel<<<B * Tx_max, 128, w.E * sizeof(float), st>>>(d_memory, w.mem_k, B * Tx_max, w.E, w.A, ctx->keys.as<float>());
+  B200_CUDA(cudaGetLastError());
+  TacoArgs a{};
+  a.memory = d_memory; a.keys = ctx->keys.as<float>(); a.lengths = d_lengths;
+  a.B = B; a.Tx_max = Tx_max; a.max_steps = max_steps; a.window = window;
+  a.rng_mode = d.mode; a.seed = d.seed; a.utt_offset = d.utterance_offset; a.masks = d.d_masks;
+  a.frames = d_frames; a.stop = d_stop; a.align = d_align; a.nsteps = d_nsteps;
+  size_t fl = 128 + w.P + (w.P + w.E + w.U) + 2 * w.U + 4 * w.U + 2 * w.U + (w.U + w.E) + w.A + 3 * kTacoMaxTx + 96 + 64 +
+              (size_t)w.KW * w.NF + (size_t)w.NF * w.A + 16384;
+  size_t smem = fl * sizeof(float);
+  B200_CUDA(cudaFuncSetAttribute(taco_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  taco_decoder_kernel<<<B, kTacoThreads, smem, st>>>(w, a);
+  B200_CUDA(cudaGetLastError());
+  ctx->launches += 2;
+  API_END
+}
+
+extern "C" int b200tts_taco_philox_masks(int device, uint64_t seed, uint64_t utterance_offset, int B, int steps, int prenet_units,
+                                         uint8_t* d_masks, void* stream) {
+  API_BEGIN
+  REQUIRE(d_masks && B >= 1 && steps >= 1 && prenet_units >= 4, B200TTS_EINVAL, "bad argument");
+  DeviceGuard dg(device);
+  size_t total = (size_t)B * steps * 2 * prenet_units;
+  unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  taco_philox_masks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, utterance_offset, B, steps, prenet_units, d_masks);
   B200_CUDA(cudaGetLastError());
   API_END
 }

@@ -1,0 +1,99 @@
+"""TacoDecoderEngine: torch-facing wrapper of the Tacotron-2 decoder context of libb200tts (one GPU)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import TacoCfg, TacoDropout
+
+DEFAULT_CFG = dict(num_mels=80, prenet_units=256, lstm_units=256, enc_dim=512, attn_dim=128, attn_filters=32,
+                   attn_kernel=31, zoneout=0.1)      # tacotron_hparams.py:99-215 of the reference
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class TacoDecoderEngine:
+    def __init__(self, weights: dict, cfg: dict | None = None, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('no CUDA device: the B200 Tacotron decoder has no CPU fallback')
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.cfg = dict(DEFAULT_CFG)
+        if cfg:
+            self.cfg.update(cfg)
+        host = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()
+                if np.asarray(v).dtype.kind == 'f' and (k.startswith('decoder/') or k.startswith('memory_layer/'))}
+        arr, keep = _lib.make_tensor_array(host)
+        c = TacoCfg()
+        for k, v in self.cfg.items():
+            setattr(c, k, v)
+        h = C.c_void_p()
+        _lib.check(self.lib.b200tts_taco_create(C.byref(h), self.device, C.byref(c), arr, len(arr)))
+        del keep
+        self._h = h
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.b200tts_taco_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self):
+        return torch.device('cuda', self.device)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def decode(self, memory, lengths=None, *, masks=None, seed=0, utterance_offset=0, max_steps=2000, window=False,
+               want_align=True):
+        """memory [B, Tx, enc_dim] (tensor/ndarray); lengths [B] or None (= Tx).  masks: optional uint8 keep flags
+        [B, max_steps, 2, prenet_units] (EXT mode) else Philox(seed).  Returns dict(frames [B,max_steps,80], stop
+        [B,max_steps], align [B,max_steps,Tx] or None, nsteps [B]) as CUDA tensors (rows beyond nsteps are undefined)."""
+        dev = self._dev()
+        m = torch.as_tensor(memory).to(device=dev, dtype=torch.float32).contiguous()
+        if m.dim() != 3 or m.shape[2] != self.cfg['enc_dim']:
+            raise ValueError(f'memory must be [B, Tx, {self.cfg["enc_dim"]}]')
+        B, Tx, _ = m.shape
+        ln = torch.full((B,), Tx, dtype=torch.int32) if lengths is None else torch.as_tensor(lengths, dtype=torch.int32)
+        if int(ln.max()) > Tx or int(ln.min()) < 1:
+            raise ValueError('lengths must be in [1, Tx]')
+        ln = ln.to(dev)
+        with torch.cuda.device(self.device):
+            frames = torch.zeros(B, max_steps, self.cfg['num_mels'], device=dev, dtype=torch.float32)
+            stop = torch.zeros(B, max_steps, device=dev, dtype=torch.float32)
+            align = torch.zeros(B, max_steps, Tx, device=dev, dtype=torch.float32) if want_align else None
+            nsteps = torch.zeros(B, device=dev, dtype=torch.int32)
+            d = TacoDropout()
+            d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            d.utterance_offset = int(utterance_offset)
+            md = None
+            if masks is not None:
+                md = torch.as_tensor(masks).to(device=dev, dtype=torch.uint8).contiguous()
+                if tuple(md.shape) != (B, max_steps, 2, self.cfg['prenet_units']):
+                    raise ValueError('masks must be [B, max_steps, 2, prenet_units]')
+                d.mode = 1
+                d.d_masks = md.data_ptr()
+            _lib.check(self.lib.b200tts_taco_decode(self._h, _ptr(m), _ptr(ln), B, Tx, C.byref(d), int(max_steps),
+                                                    1 if window else 0, _ptr(frames), _ptr(stop), _ptr(align), _ptr(nsteps),
+                                                    self._stream()))
+            for t in (m, ln, md):
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream(self.device))
+        return dict(frames=frames, stop=stop, align=align, nsteps=nsteps)
+
+    def philox_masks(self, seed, utterance_offset, B, steps):
+        with torch.cuda.device(self.device):
+            m = torch.empty(B, steps, 2, self.cfg['prenet_units'], device=self._dev(), dtype=torch.uint8)
+            _lib.check(self.lib.b200tts_taco_philox_masks(self.device, int(seed) & 0xFFFFFFFFFFFFFFFF, int(utterance_offset),
+                                                          B, steps, self.cfg['prenet_units'], _ptr(m), self._stream()))
+        return m
