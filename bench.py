@@ -170,7 +170,8 @@ def main():
     mels_host = synth.synth_mels(1236 + rank, B, T)                       # this rank's shard of the global batch
     mels_dev = torch.as_tensor(mels_host).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)   # > 126 MB L2
-    gathered = [torch.empty(B, S, device=dev, dtype=torch.int16) for _ in range(N)] if N > 1 else None
+    # NCCL has no int16: the labels travel as raw bytes
+    gathered = [torch.empty(B, S * 2, device=dev, dtype=torch.uint8) for _ in range(N)] if N > 1 else None
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -182,7 +183,7 @@ def main():
         flush.fill_(float(i))                                              # evict L2 between iterations
         out = eng.generate(mels_dev, seed=20260923, utterance_offset=rank * B, kernel=args.kernel)
         if N > 1:
-            dist.all_gather(gathered, out['labels'])
+            dist.all_gather(gathered, out['labels'].view(torch.uint8))
         return out
 
     for i in range(args.warmup):
