@@ -12,6 +12,7 @@
  *   b200tts_wavernn_generate   <- WaveRNN.generate (unbatched branch)   wavernn/models/fatchord_version.py:169-264
  *                                 incl. decode_mu_law                   wavernn/utils/dsp.py:98-103
  *   b200tts_wavernn_generate_host  same, HOST buffers in/out (what wavernn_gen.py:41 sees end to end)
+ *   gen_opts.fold_target/_overlap  <- fold_with_overlap + xfade_and_unfold  fatchord_version.py:293-405 (--batched)
  *
  * Conventions
  *   - plain C types only; no torch / CUDA types in any signature (`stream` is a cudaStream_t passed as void*).
@@ -94,6 +95,12 @@ typedef struct {
   const int16_t* d_teacher;   /* optional [B][S]: fed back instead of the sampled label (teacher forcing) */
   float* d_logits;            /* optional [S][B][n_classes]: fc3 outputs of every step (debug / parity) */
   int32_t max_steps;          /* 0 = all S = T*hop steps; otherwise stop early (no wave is produced)   */
+  int32_t fold_target;        /* > 0: fold-with-overlap batched generation of ONE utterance (fatchord_version.py:188-190,
+                                 :250-251, :293-405; hp.voc_target).  Then B must be 1, d_labels (if given) is
+                                 [n_folds][fold_len] (see b200tts_wavernn_fold_geometry) and d_wave is the cross-faded wave */
+  int32_t fold_overlap;       /* hp.voc_overlap                                                          */
+  const int32_t* d_utt_frames;/* optional [B]: true frame count of each row of a zero-padded ragged batch; row b of d_wave is then
+                                 truncated and faded at (frames_b - 1)*hop like a batch-1 run, and zero beyond      */
 } b200tts_gen_opts;
 
 typedef struct b200tts_wavernn b200tts_wavernn;
@@ -118,6 +125,9 @@ int b200tts_wavernn_upsample(b200tts_wavernn* ctx, const float* d_mel, int B, in
  * truncated and faded exactly like fatchord_version.py:243-258 (may be NULL).  Needs T >= 21 when d_wave != NULL. */
 int b200tts_wavernn_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
                              const b200tts_gen_opts* opts, int16_t* d_labels, double* d_wave, void* stream);
+
+/* n_folds and fold_len = target + 2*overlap of fold_with_overlap (fatchord_version.py:319-330) for a T-frame utterance. */
+int b200tts_wavernn_fold_geometry(int T, int hop, int target, int overlap, int* n_folds, int* fold_len);
 
 /* Same with HOST buffers: copies h_mel to the device, generates, copies labels / wave back, synchronises. */
 int b200tts_wavernn_generate_host(b200tts_wavernn* ctx, const float* h_mel, int B, int T, const b200tts_rng* rng,
@@ -173,6 +183,17 @@ void b200tts_taco_destroy(b200tts_taco* ctx);
 int b200tts_taco_decode(b200tts_taco* ctx, const float* d_memory, const int32_t* d_lengths, int B, int Tx_max,
                         const b200tts_taco_dropout* dropout, int max_steps, int window, float* d_frames, float* d_stop,
                         float* d_align, int32_t* d_nsteps, void* stream);
+
+/* Run-once neighbours of the decoder loop (available when b200tts_taco_create also received the encoder / postnet
+ * variables):
+ *   b200tts_taco_encode   <- embedding lookup + EncoderConvolutions + EncoderRNN   tacotron.py:44-57, modules.py:145-217
+ *   b200tts_taco_postnet  <- clip + Postnet + postnet_projection + residual + clip  tacotron.py:111-129, modules.py:345-376
+ * d_ids [B][Tx_max] symbol ids (tacotron/utils/text.py:18-31), d_memory [B][Tx_max][enc_dim];
+ * d_frames [B][max_steps][num_mels] raw decoder outputs, d_nsteps [B], d_mel [B][max_steps][num_mels] (rows >= nsteps untouched). */
+int b200tts_taco_encode(b200tts_taco* ctx, const int32_t* d_ids, const int32_t* d_lengths, int B, int Tx_max, float* d_memory,
+                        void* stream);
+int b200tts_taco_postnet(b200tts_taco* ctx, const float* d_frames, const int32_t* d_nsteps, int B, int max_steps, float* d_mel,
+                         void* stream);
 
 /* The keep flags the PHILOX dropout mode draws: d_masks [B][steps][2][prenet_units]. */
 int b200tts_taco_philox_masks(int device, uint64_t seed, uint64_t utterance_offset, int B, int steps, int prenet_units,

@@ -80,6 +80,23 @@ def make_case(name, model, mel_seed, noise_seed, B, T, logit_steps, store_upsamp
           f'-> {os.path.getsize(path) / 1e3:.0f} kB')
 
 
+def make_batched_case(name, model, mel_seed, noise_seed, T, target, overlap):
+    """generate(batched=True): fold-with-overlap of ONE utterance (fatchord_version.py:188-190, :250-251)."""
+    mels = synth.synth_mels(mel_seed, 1, T)
+    S = T * 275
+    nf = (S - overlap) // (target + overlap)
+    if S - (nf * (target + overlap) + overlap) != 0:
+        nf += 1
+    L = target + 2 * overlap
+    q = synth.synth_exponential_noise(noise_seed, L, nf)
+    res = rh.reference_generate(model, mels, q, batched=True, target=target, overlap=overlap)
+    assert res['labels'].shape == (nf, L), res['labels'].shape
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, mel_seed=mel_seed, noise_seed=noise_seed, T=T, target=target, overlap=overlap,
+                        labels=res['labels'], wave=res['wave0'])
+    print(f'  {name}: folds {nf} x {L}, wave {res["wave0"].shape} -> {os.path.getsize(path) / 1e3:.0f} kB')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -91,9 +108,11 @@ def main():
     steps80 = [0, 1, 2, 275, 5000, 10000, 15000, 21999]
     make_case('wavernn_ckpt_T80', ck, mel_seed=1234, noise_seed=202, B=1, T=80, logit_steps=steps80,
               store_upsample=False)
+    make_batched_case('wavernn_ckpt_batched_T30', ck, mel_seed=103, noise_seed=204, T=30, target=2700, overlap=500)
     print('synthetic-weights model (portable)')
     sy = rh.build_model(synth.synth_state_dict(11))
     make_case('wavernn_synth_T24', sy, mel_seed=102, noise_seed=203, B=2, T=24, logit_steps=steps24)
+    make_batched_case('wavernn_synth_batched_T30', sy, mel_seed=104, noise_seed=205, T=30, target=2750, overlap=550)
 
 
 if __name__ == '__main__':

@@ -101,7 +101,7 @@ class _RaceCategorical:
         return lab
 
 
-def reference_generate(model, mels, q, capture_logits_at=()):
+def reference_generate(model, mels, q, capture_logits_at=(), batched=False, target=None, overlap=None):
     """Runs the reference `generate` (fatchord_version.py:169) unbatched with injected noise.
 
     Returns dict(wave0 float64 [wave_len] (utterance 0 only -- :253), labels [B,S] int16, logits {step: [B,ncls]}).
@@ -124,7 +124,8 @@ def reference_generate(model, mels, q, capture_logits_at=()):
     torch.distributions.Categorical = _RaceCategorical
     try:
         hp = fv._hp
-        wave = model.generate(torch.as_tensor(mels), '/dev/null', False, hp.voc_target, hp.voc_overlap, hp.mu_law)
+        wave = model.generate(torch.as_tensor(mels), '/dev/null', bool(batched), target if target is not None else hp.voc_target,
+                              overlap if overlap is not None else hp.voc_overlap, hp.mu_law)
     finally:
         torch.distributions.Categorical = orig
         h.remove()

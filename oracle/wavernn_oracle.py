@@ -248,6 +248,85 @@ def generate(p, mels, q=None, teacher=None, keep_logits=None, mu_law=True, seed=
     return dict(labels=labels, wave=wave, logits=kept, seconds=seconds, steps=S)
 
 
+def fold_with_overlap(x, target, overlap):
+    """fatchord_version.py:293-340.  x [1, S, F] -> [num_folds, target + 2*overlap, F]."""
+    _, total_len, feats = x.shape
+    num_folds = (total_len - overlap) // (target + overlap)
+    extended_len = num_folds * (overlap + target) + overlap
+    remaining = total_len - extended_len
+    if remaining != 0:
+        num_folds += 1
+        padding = target + 2 * overlap - remaining
+        x = pad_tensor(x, padding, side='after')
+    folded = np.zeros((num_folds, target + 2 * overlap, feats), dtype=x.dtype)
+    for i in range(num_folds):
+        start = i * (target + overlap)
+        folded[i] = x[0, start:start + target + 2 * overlap, :]
+    return folded
+
+
+def xfade_and_unfold(y, target, overlap):
+    """fatchord_version.py:342-405.  y float64 [num_folds, target + 2*overlap] (modified in place like the reference)."""
+    num_folds, length = y.shape
+    target = length - 2 * overlap
+    total_len = num_folds * (target + overlap) + overlap
+    silence_len = overlap // 2
+    fade_len = overlap - silence_len
+    t = np.linspace(-1, 1, fade_len, dtype=np.float64)
+    fade_in = np.concatenate([np.zeros(silence_len), np.sqrt(0.5 * (1 + t))])
+    fade_out = np.concatenate([np.ones(silence_len), np.sqrt(0.5 * (1 - t))])
+    y[:, :overlap] *= fade_in
+    y[:, -overlap:] *= fade_out
+    unfolded = np.zeros(total_len, dtype=np.float64)
+    for i in range(num_folds):
+        start = i * (target + overlap)
+        unfolded[start:start + target + 2 * overlap] += y[i]
+    return unfolded
+
+
+def generate_batched(p, mel, target, overlap, q=None, mu_law=True, seed=0, teacher=None, keep_logits=(), max_steps=None):
+    """WaveRNN.generate(batched=True), fatchord_version.py:169-264: ONE utterance mel [1, feat, T]; q [L, num_folds, ncls].
+    Returns dict(labels [num_folds, L], wave [wave_len] float64, seconds)."""
+    d = _dims(p)
+    pf = {k: (v.astype(F32) if v.dtype.kind == 'f' else v) for k, v in p.items()}
+    mel = np.asarray(mel, dtype=F32)
+    assert mel.shape[0] == 1
+    T = mel.shape[2]
+    hop = d['hop']
+    wave_len = (T - 1) * hop
+    t0 = time.perf_counter()
+    mp = pad_tensor(mel.transpose(0, 2, 1), d['pad'], 'both').transpose(0, 2, 1)
+    m_up, aux = upsample(pf, mp)
+    m_up = fold_with_overlap(m_up, target, overlap)                                          # :189
+    aux = fold_with_overlap(aux, target, overlap)                                            # :190
+    B, S, _ = m_up.shape
+    A = d['aux']
+    h1 = np.zeros((B, d['rnn']), dtype=F32)
+    h2 = np.zeros((B, d['rnn']), dtype=F32)
+    x = np.zeros((B, 1), dtype=F32)
+    labels = np.zeros((B, S), dtype=np.int16)
+    rs = np.random.RandomState(seed) if q is None else None
+    kept = {}
+    for i in range(S if max_steps is None else min(S, max_steps)):
+        a = aux[:, i, :]
+        logits, h1, h2 = step_logits(pf, x, m_up[:, i, :], a[:, :A], a[:, A:2 * A], a[:, 2 * A:3 * A], a[:, 3 * A:4 * A], h1, h2)
+        if i in keep_logits:
+            kept[i] = logits.copy()
+        qi = q[i] if q is not None else np.maximum(rs.standard_exponential(size=logits.shape).astype(F32), F32(1e-30))
+        lab = sample_race(softmax(logits), qi)
+        labels[:, i] = lab
+        fb = teacher[:, i].astype(np.int64) if teacher is not None else lab
+        x = label_to_float(fb, d['ncls'])[:, None]
+    out = label_to_float(labels, d['ncls']).astype(np.float64)
+    if mu_law:
+        out = decode_mu_law(out, d['ncls'])
+    out = xfade_and_unfold(out, target, overlap)                                             # :251
+    fade = np.linspace(1, 0, 20 * hop)
+    out = out[:wave_len].copy()
+    out[-20 * hop:] *= fade
+    return dict(labels=labels, wave=out, seconds=time.perf_counter() - t0, logits=kept)
+
+
 def finish_wave(labels, ncls, wave_len, hop, mu_law=True):
     """generate() epilogue, fatchord_version.py:243-258: float64, mu-law decode, truncate, 20-hop fade-out."""
     out = label_to_float(np.asarray(labels), ncls).astype(np.float64)                      # :243-245

@@ -42,7 +42,7 @@ class Rng(C.Structure):
 
 class GenOpts(C.Structure):
     _fields_ = [('kernel', C.c_int32), ('mu_law', C.c_int32), ('d_teacher', C.c_void_p), ('d_logits', C.c_void_p),
-                ('max_steps', C.c_int32)]
+                ('max_steps', C.c_int32), ('fold_target', C.c_int32), ('fold_overlap', C.c_int32), ('d_utt_frames', C.c_void_p)]
 
 
 class TacoCfg(C.Structure):
@@ -65,6 +65,7 @@ SIGNATURES = {
                                            C.c_void_p]),
     'b200tts_wavernn_generate': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Rng), C.POINTER(GenOpts),
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    'b200tts_wavernn_fold_geometry': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'b200tts_wavernn_generate_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Rng),
                                                 C.POINTER(GenOpts), C.c_void_p, C.c_void_p]),
     'b200tts_philox_exponential': (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -76,6 +77,8 @@ SIGNATURES = {
     'b200tts_taco_destroy': (None, [C.c_void_p]),
     'b200tts_taco_decode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(TacoDropout), C.c_int,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'b200tts_taco_encode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'b200tts_taco_postnet': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'b200tts_taco_philox_masks': (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 

@@ -15,6 +15,7 @@
 #include "wavernn_utt.cuh"
 #include "wavernn_grid.cuh"
 #include "taco_decoder.cuh"
+#include "taco_encpost.cuh"
 
 using namespace b200tts;
 
@@ -151,7 +152,7 @@ struct b200tts_wavernn {
   ResnetParams rp{};
   const float* d_fir = nullptr;   // [hop][NT]
   GridModel gm{};                 // per-CTA weight blobs of the grid kernel
-  DeviceBuf grid_blob, mels_T, aux_T, grid_sync, grid_prof;
+  DeviceBuf grid_blob, mels_T, aux_T, grid_sync, grid_prof, fold_mels, fold_aux;
   int last_grid_ncta = 0;
   int coop = 0;
   // scratch
@@ -428,6 +429,8 @@ extern "C" void b200tts_wavernn_destroy(b200tts_wavernn* ctx) {
   ctx->aux_T.release();
   ctx->grid_sync.release();
   ctx->grid_prof.release();
+  ctx->fold_mels.release();
+  ctx->fold_aux.release();
   ctx->h_stage.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -545,7 +548,25 @@ static int grid_variant(int B, int* variant) {
   return (B + 255) / 256 * 256;
 }
 
-static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cudaStream_t st) {
+struct FoldGeom {           // fold_with_overlap geometry (fatchord_version.py:319-330)
+  int nfold, L, stride, total_len;
+};
+static FoldGeom fold_geometry(int S, int target, int overlap) {
+  FoldGeom g{};
+  g.stride = target + overlap;
+  g.L = target + 2 * overlap;
+  int num_folds = (S - overlap) / g.stride;
+  int extended = num_folds * g.stride + overlap;
+  if (S - extended != 0) num_folds += 1;
+  g.nfold = num_folds;
+  g.total_len = num_folds * g.stride + overlap;
+  return g;
+}
+
+// `fold` != null: `ua` already describes the folded problem (B = nfold, S = T = L, hop = 1) and the conditioning of the
+// single source utterance is in ctx->mels_up [S0][feat] / ctx->aux_frames [T0][O].
+static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cudaStream_t st, const FoldGeom* fold = nullptr,
+                        int S0 = 0) {
   const b200tts_wavernn_cfg& c = ctx->cfg;
   const GridModel& g = ctx->gm;
   REQUIRE(g.ok, B200TTS_EINVAL, "this model/device cannot run the grid kernel (use B200TTS_KERNEL_UTTERANCE)");
@@ -555,7 +576,14 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   // conditioning in K-major layout
   ctx->mels_T.ensure((size_t)S * c.feat_dims * Bp * sizeof(float));
   ctx->aux_T.ensure((size_t)T * O * Bp * sizeof(float));
-  {
+  if (fold) {
+    size_t n = (size_t)S * (c.feat_dims + O) * Bp;
+    unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 32);
+    fold_cond_T_kernel<<<grid, 256, 0, st>>>(ctx->mels_up.as<float>(), ctx->aux_frames.as<float>(), S0, c.hop_length, c.feat_dims, O,
+                                             fold->L, fold->stride, fold->nfold, Bp, ctx->mels_T.as<float>(), ctx->aux_T.as<float>());
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  } else {
     size_t n = (size_t)S * c.feat_dims * Bp;
     unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 32);
     mel_fir_T_kernel<<<grid, 256, 0, st>>>(d_mel, ctx->d_fir, B, Bp, T, c.feat_dims, c.hop_length, c.pad, ctx->NT,
@@ -631,14 +659,26 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
   int kernel = o.kernel;
   if (kernel == B200TTS_KERNEL_AUTO) kernel = ctx->gm.ok ? B200TTS_KERNEL_GRID : B200TTS_KERNEL_UTTERANCE;
   REQUIRE(kernel == B200TTS_KERNEL_UTTERANCE || kernel == B200TTS_KERNEL_GRID, B200TTS_EINVAL, "unknown kernel selector");
+  const bool folding = o.fold_target > 0;
+  FoldGeom fg{};
+  if (folding) {
+    REQUIRE(B == 1, B200TTS_EINVAL, "fold-with-overlap generation takes exactly one utterance (the reference folds x[0] only)");
+    REQUIRE(o.fold_overlap >= 2 && o.fold_target >= 1, B200TTS_EINVAL, "fold target/overlap out of range");
+    REQUIRE(steps == S, B200TTS_EINVAL, "max_steps is not supported together with folding");
+    REQUIRE(S > o.fold_overlap, B200TTS_EINVAL, "utterance shorter than the fold overlap");
+    fg = fold_geometry(S, o.fold_target, o.fold_overlap);
+    REQUIRE(fg.nfold >= 1 && fg.nfold <= 65535, B200TTS_EINVAL, "fold count out of range");
+  }
+  const int GB = folding ? fg.nfold : B;            // rows the generation kernels see
+  const int GS = folding ? fg.L : S;                // steps per row
   ctx->aux_frames.ensure((size_t)B * T * O * sizeof(float));
   int16_t* labels = d_labels;
   if (!labels) {
-    ctx->labels.ensure((size_t)B * S * sizeof(int16_t));
+    ctx->labels.ensure((size_t)GB * GS * sizeof(int16_t));
     labels = ctx->labels.as<int16_t>();
   }
   float* mels_up = nullptr;
-  if (kernel == B200TTS_KERNEL_UTTERANCE) {
+  if (kernel == B200TTS_KERNEL_UTTERANCE || folding) {
     ctx->mels_up.ensure((size_t)B * S * c.feat_dims * sizeof(float));
     mels_up = ctx->mels_up.as<float>();
   }
@@ -647,29 +687,56 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
   GenArgs a{};
   a.mels_up = ctx->mels_up.as<float>();
   a.aux_frames = ctx->aux_frames.as<float>();
-  a.B = B; a.S = S; a.T = T; a.hop = hop; a.steps = steps;
+  a.B = GB; a.S = GS; a.T = folding ? GS : T; a.hop = folding ? 1 : hop; a.steps = folding ? GS : steps;
   a.rng_mode = r.mode; a.seed = r.seed; a.utt_offset = r.utterance_offset; a.q = r.d_q;
   a.teacher = o.d_teacher; a.logits_out = o.d_logits; a.labels = labels;
 
   if (kernel == B200TTS_KERNEL_UTTERANCE) {
+    if (folding) {   // per-fold conditioning in the row-major layout this kernel reads, aux per sample (hop = 1)
+      ctx->fold_mels.ensure((size_t)GB * GS * c.feat_dims * sizeof(float));
+      ctx->fold_aux.ensure((size_t)GB * GS * O * sizeof(float));
+      size_t n = (size_t)GB * GS * (c.feat_dims + O);
+      unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 32);
+      fold_cond_kernel<<<grid, 256, 0, st>>>(ctx->mels_up.as<float>(), ctx->aux_frames.as<float>(), S, hop, c.feat_dims, O, fg.L,
+                                             fg.stride, fg.nfold, ctx->fold_mels.as<float>(), ctx->fold_aux.as<float>());
+      B200_CUDA(cudaGetLastError());
+      ctx->launches++;
+      a.mels_up = ctx->fold_mels.as<float>();
+      a.aux_frames = ctx->fold_aux.as<float>();
+    }
     B200_CUDA(cudaEventRecord(ctx->ev0, st));
     // utterances per CTA: enough CTAs to cover the SMs first, then amortise the L2 weight stream over more rows
-    int per = (B + ctx->sm_count - 1) / ctx->sm_count;
+    int per = (GB + ctx->sm_count - 1) / ctx->sm_count;
     if (per <= 1) launch_utt<1>(ctx, a, st);
     else if (per <= 2) launch_utt<2>(ctx, a, st);
     else if (per <= 4) launch_utt<4>(ctx, a, st);
     else launch_utt<8>(ctx, a, st);
     B200_CUDA(cudaEventRecord(ctx->ev1, st));
   } else {
-    launch_grid(ctx, d_mel, a, st);
+    launch_grid(ctx, d_mel, a, st, folding ? &fg : nullptr, S);
   }
   ctx->ev_valid = true;
   if (d_wave) {
-    dim3 grid((wave_len + 255) / 256, B);
-    finish_wave_kernel<<<grid, 256, 0, st>>>(labels, S, wave_len, fade_len, ctx->NC, o.mu_law, d_wave);
+    if (folding) {
+      xfade_unfold_kernel<<<(wave_len + 255) / 256, 256, 0, st>>>(labels, fg.nfold, fg.L, o.fold_target, o.fold_overlap, wave_len,
+                                                                  fade_len, ctx->NC, o.mu_law, d_wave);
+    } else {
+      dim3 grid((wave_len + 255) / 256, B);
+      finish_wave_kernel<<<grid, 256, 0, st>>>(labels, S, wave_len, fade_len, ctx->NC, o.mu_law, o.d_utt_frames, hop, d_wave);
+    }
     B200_CUDA(cudaGetLastError());
     ctx->launches++;
   }
+}
+
+extern "C" int b200tts_wavernn_fold_geometry(int T, int hop, int target, int overlap, int* n_folds, int* fold_len) {
+  API_BEGIN
+  REQUIRE(T >= 1 && hop >= 1 && target >= 1 && overlap >= 2 && n_folds && fold_len, B200TTS_EINVAL, "bad argument");
+  REQUIRE(T * hop > overlap, B200TTS_EINVAL, "utterance shorter than the fold overlap");
+  FoldGeom g = fold_geometry(T * hop, target, overlap);
+  *n_folds = g.nfold;
+  *fold_len = g.L;
+  API_END
 }
 
 extern "C" int b200tts_wavernn_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
@@ -689,6 +756,7 @@ extern "C" int b200tts_wavernn_generate_host(b200tts_wavernn* ctx, const float* 
   REQUIRE(B >= 1 && T >= 1 && B <= 65535, B200TTS_EINVAL, "B must be 1..65535 and T positive");
   REQUIRE(!opts || (!opts->d_teacher && !opts->d_logits), B200TTS_EINVAL, "device-side debug buffers need the device entry point");
   REQUIRE(!rng || rng->mode == B200TTS_RNG_PHILOX, B200TTS_EINVAL, "the host entry point only takes the PHILOX mode");
+  REQUIRE(!opts || opts->fold_target == 0 || !h_labels, B200TTS_EINVAL, "folded generation returns only the wave through the host entry point");
   DeviceGuard dg(ctx->device);
   const b200tts_wavernn_cfg& c = ctx->cfg;
   const size_t S = (size_t)T * c.hop_length, wave_len = (size_t)(T - 1) * c.hop_length;
@@ -766,11 +834,23 @@ extern "C" int b200tts_philox_exponential(int device, uint64_t seed, uint64_t ut
 // ================================================================================================================
 // Tacotron-2 decoder
 // ================================================================================================================
+struct TacoConvW {          // one conv1d + folded BatchNorm
+  const float *K, *bias, *scale, *shift;
+  int k, Cin, Cout;
+};
 struct b200tts_taco {
   int device = 0;
   b200tts_taco_cfg cfg{};
-  DeviceBuf weights, keys;
+  DeviceBuf weights, keys, act_a, act_b;
   TacoWeights tw{};
+  // run-once neighbours (present when the weight list carried them)
+  bool has_encoder = false, has_postnet = false;
+  const float* embedding = nullptr;
+  int vocab = 0, emb_dim = 0, enc_units = 0;
+  TacoConvW enc_conv[3]{}, post_conv[5]{};
+  const float *enc_kfw = nullptr, *enc_bfw = nullptr, *enc_kbw = nullptr, *enc_bbw = nullptr;
+  const float *post_pk = nullptr, *post_pb = nullptr;
+  int post_channels = 0;
   int64_t launches = 0;
 };
 
@@ -822,6 +902,53 @@ extern "C" int b200tts_taco_create(b200tts_taco** out, int device, const b200tts
   o[18] = copy(D + "stop_token_projection/projection_stop_token_projection/kernel", {U + E, 1});
   o[19] = copy(D + "stop_token_projection/projection_stop_token_projection/bias", {1});
   o[20] = copy("memory_layer/kernel", {E, AD});
+  // ---- optional run-once neighbours: encoder and postnet ----
+  struct ConvOff { size_t K, bias, scale, shift; int k, Cin, Cout; };
+  auto pack_conv = [&](const std::string& scope) {
+    auto it = tm.find(scope + "/conv1d/kernel");
+    REQUIRE(it != tm.end() && it->second->ndim == 3, B200TTS_EMISSING, "missing weight tensor '" + scope + "/conv1d/kernel'");
+    const b200tts_tensor* kt = it->second;
+    ConvOff c{};
+    c.k = (int)kt->shape[0]; c.Cin = (int)kt->shape[1]; c.Cout = (int)kt->shape[2];
+    c.K = copy(scope + "/conv1d/kernel", {c.k, c.Cin, c.Cout});
+    c.bias = copy(scope + "/conv1d/bias", {c.Cout});
+    const float* g = need(tm, scope + "/batch_normalization/gamma", {c.Cout})->data;
+    const float* be = need(tm, scope + "/batch_normalization/beta", {c.Cout})->data;
+    const float* mu = need(tm, scope + "/batch_normalization/moving_mean", {c.Cout})->data;
+    const float* var = need(tm, scope + "/batch_normalization/moving_variance", {c.Cout})->data;
+    c.scale = pk.add(c.Cout); c.shift = pk.add(c.Cout);
+    for (int i = 0; i < c.Cout; ++i) {                 // tf.layers.batch_normalization, moving stats, epsilon 1e-3
+      double sc = (double)g[i] / std::sqrt((double)var[i] + 1e-3);
+      pk.h[c.scale + i] = (float)sc;
+      pk.h[c.shift + i] = (float)((double)be[i] - (double)mu[i] * sc);
+    }
+    return c;
+  };
+  ConvOff encc[3]{}, postc[5]{};
+  size_t o_emb = 0, o_kfw = 0, o_bfw = 0, o_kbw = 0, o_bbw = 0, o_pk = 0, o_pb = 0;
+  if (tm.count("inputs_embedding") && tm.count("encoder_convolutions/conv_layer_1_encoder_convolutions/conv1d/kernel")) {
+    const b200tts_tensor* et = tm["inputs_embedding"];
+    REQUIRE(et->ndim == 2, B200TTS_ESHAPE, "inputs_embedding must be 2-D");
+    ctx->vocab = (int)et->shape[0]; ctx->emb_dim = (int)et->shape[1];
+    o_emb = copy("inputs_embedding", {ctx->vocab, ctx->emb_dim});
+    for (int i = 0; i < 3; ++i) encc[i] = pack_conv("encoder_convolutions/conv_layer_" + std::to_string(i + 1) + "_encoder_convolutions");
+    REQUIRE(encc[0].Cin == ctx->emb_dim && encc[2].Cout % 4 == 0 && E % 2 == 0, B200TTS_ESHAPE, "encoder conv shapes");
+    const int EU = E / 2, CI = encc[2].Cout;
+    REQUIRE(4 * EU == 1024, B200TTS_EINVAL, "encoder LSTM units must be 256");
+    const std::string LS = "encoder_LSTM/bidirectional_rnn/";
+    o_kfw = copy(LS + "fw/encoder_fw_LSTM/kernel", {CI + EU, 4 * EU}); o_bfw = copy(LS + "fw/encoder_fw_LSTM/bias", {4 * EU});
+    o_kbw = copy(LS + "bw/encoder_bw_LSTM/kernel", {CI + EU, 4 * EU}); o_bbw = copy(LS + "bw/encoder_bw_LSTM/bias", {4 * EU});
+    ctx->enc_units = EU;
+    ctx->has_encoder = true;
+  }
+  if (tm.count("postnet_projection/projection_postnet_projection/kernel")) {
+    for (int i = 0; i < 5; ++i) postc[i] = pack_conv("postnet_convolutions/conv_layer_" + std::to_string(i + 1) + "_postnet_convolutions");
+    REQUIRE(postc[0].Cin == M, B200TTS_ESHAPE, "postnet conv 1 must take num_mels channels");
+    ctx->post_channels = postc[4].Cout;
+    o_pk = copy("postnet_projection/projection_postnet_projection/kernel", {ctx->post_channels, M});
+    o_pb = copy("postnet_projection/projection_postnet_projection/bias", {M});
+    ctx->has_postnet = true;
+  }
   ctx->weights.ensure(pk.h.size() * sizeof(float));
   B200_CUDA(cudaMemcpy(ctx->weights.p, pk.h.data(), pk.h.size() * sizeof(float), cudaMemcpyHostToDevice));
   const float* b = ctx->weights.as<float>();
@@ -832,6 +959,16 @@ extern "C" int b200tts_taco_create(b200tts_taco** out, int device, const b200tts
   w.mu_k = b + o[14]; w.mu_b = b + o[15]; w.fr_k = b + o[16]; w.fr_b = b + o[17]; w.st_k = b + o[18]; w.st_b = b + o[19];
   w.mem_k = b + o[20];
   w.mels = M; w.P = P; w.U = U; w.E = E; w.A = AD; w.NF = NF; w.KW = KW; w.zoneout = c.zoneout;
+  auto bind = [&](const ConvOff& c0) { return TacoConvW{b + c0.K, b + c0.bias, b + c0.scale, b + c0.shift, c0.k, c0.Cin, c0.Cout}; };
+  if (ctx->has_encoder) {
+    ctx->embedding = b + o_emb;
+    for (int i = 0; i < 3; ++i) ctx->enc_conv[i] = bind(encc[i]);
+    ctx->enc_kfw = b + o_kfw; ctx->enc_bfw = b + o_bfw; ctx->enc_kbw = b + o_kbw; ctx->enc_bbw = b + o_bbw;
+  }
+  if (ctx->has_postnet) {
+    for (int i = 0; i < 5; ++i) ctx->post_conv[i] = bind(postc[i]);
+    ctx->post_pk = b + o_pk; ctx->post_pb = b + o_pb;
+  }
   cleanup.c = nullptr;
   *out = ctx;
   API_END
@@ -844,6 +981,8 @@ extern "C" void b200tts_taco_destroy(b200tts_taco* ctx) {
   cudaSetDevice(ctx->device);
   ctx->weights.release();
   ctx->keys.release();
+  ctx->act_a.release();
+  ctx->act_b.release();
   if (prev >= 0) cudaSetDevice(prev);
   delete ctx;
 }
@@ -888,5 +1027,70 @@ extern "C" int b200tts_taco_philox_masks(int device, uint64_t seed, uint64_t utt
   unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
   taco_philox_masks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, utterance_offset, B, steps, prenet_units, d_masks);
   B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+static void taco_launch_conv(b200tts_taco* ctx, const TacoConvW& cw, const float* x, const int* ids, const int* lengths, int B, int Tmax,
+                             int act, bool clip_in, float lo, float hi, float* y, cudaStream_t st) {
+  ConvArgs a{};
+  a.x = x; a.ids = ids; a.table = ctx->embedding; a.lengths = lengths;
+  a.K = cw.K; a.bias = cw.bias; a.bn_scale = cw.scale; a.bn_shift = cw.shift; a.y = y;
+  a.Tmax = Tmax; a.Cin = cw.Cin; a.Cout = cw.Cout; a.k = cw.k; a.act = act; a.clip_in = clip_in ? 1 : 0; a.lo = lo; a.hi = hi;
+  size_t smem = (size_t)(kConvTile + cw.k - 1) * cw.Cin * sizeof(float);
+  dim3 grid((Tmax + kConvTile - 1) / kConvTile, B);
+  taco_conv_bn_kernel<<<grid, 256, smem, st>>>(a);
+  B200_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+extern "C" int b200tts_taco_encode(b200tts_taco* ctx, const int32_t* d_ids, const int32_t* d_lengths, int B, int Tx_max, float* d_memory,
+                                   void* stream) {
+  API_BEGIN
+  REQUIRE(ctx && d_ids && d_lengths && d_memory, B200TTS_EINVAL, "null argument");
+  REQUIRE(ctx->has_encoder, B200TTS_EMISSING, "this context was created without the encoder variables");
+  REQUIRE(B >= 1 && Tx_max >= 1 && Tx_max <= kTacoMaxTx, B200TTS_EINVAL, "B / Tx_max out of range");
+  DeviceGuard dg(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = ctx->enc_conv[0].Cout;
+  ctx->act_a.ensure((size_t)B * Tx_max * C * sizeof(float));
+  ctx->act_b.ensure((size_t)B * Tx_max * C * sizeof(float));
+  float* a = ctx->act_a.as<float>();
+  float* bb = ctx->act_b.as<float>();
+  taco_launch_conv(ctx, ctx->enc_conv[0], nullptr, d_ids, d_lengths, B, Tx_max, 1, false, 0.f, 0.f, a, st);
+  taco_launch_conv(ctx, ctx->enc_conv[1], a, nullptr, d_lengths, B, Tx_max, 1, false, 0.f, 0.f, bb, st);
+  taco_launch_conv(ctx, ctx->enc_conv[2], bb, nullptr, d_lengths, B, Tx_max, 1, false, 0.f, 0.f, a, st);
+  const int U = ctx->enc_units, Cin = ctx->enc_conv[2].Cout;
+  size_t smem = ((size_t)(Cin + U) + 4 * U + U + 4 * 4 * U) * sizeof(float);
+  B200_CUDA(cudaFuncSetAttribute(taco_bilstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  taco_bilstm_kernel<<<dim3(B, 2), kTacoThreads, smem, st>>>(a, d_lengths, Tx_max, Cin, U, ctx->enc_kfw, ctx->enc_bfw, ctx->enc_kbw,
+                                                              ctx->enc_bbw, ctx->cfg.zoneout, d_memory);
+  B200_CUDA(cudaGetLastError());
+  ctx->launches++;
+  API_END
+}
+
+extern "C" int b200tts_taco_postnet(b200tts_taco* ctx, const float* d_frames, const int32_t* d_nsteps, int B, int max_steps, float* d_mel,
+                                    void* stream) {
+  API_BEGIN
+  REQUIRE(ctx && d_frames && d_nsteps && d_mel, B200TTS_EINVAL, "null argument");
+  REQUIRE(ctx->has_postnet, B200TTS_EMISSING, "this context was created without the postnet variables");
+  REQUIRE(B >= 1 && max_steps >= 1, B200TTS_EINVAL, "B / max_steps out of range");
+  DeviceGuard dg(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = ctx->post_channels, M = ctx->cfg.num_mels;
+  const float lo = -4.0f - 0.1f, hi = 4.0f;       // T2_output_range[0] - lower_bound_decay, T2_output_range[1] (tacotron.py:33,111-112)
+  ctx->act_a.ensure((size_t)B * max_steps * C * sizeof(float));
+  ctx->act_b.ensure((size_t)B * max_steps * C * sizeof(float));
+  float* a = ctx->act_a.as<float>();
+  float* bb = ctx->act_b.as<float>();
+  taco_launch_conv(ctx, ctx->post_conv[0], d_frames, nullptr, d_nsteps, B, max_steps, 2, true, lo, hi, a, st);
+  taco_launch_conv(ctx, ctx->post_conv[1], a, nullptr, d_nsteps, B, max_steps, 2, false, 0.f, 0.f, bb, st);
+  taco_launch_conv(ctx, ctx->post_conv[2], bb, nullptr, d_nsteps, B, max_steps, 2, false, 0.f, 0.f, a, st);
+  taco_launch_conv(ctx, ctx->post_conv[3], a, nullptr, d_nsteps, B, max_steps, 2, false, 0.f, 0.f, bb, st);
+  taco_launch_conv(ctx, ctx->post_conv[4], bb, nullptr, d_nsteps, B, max_steps, 0, false, 0.f, 0.f, a, st);
+  taco_postnet_proj_kernel<<<dim3(max_steps, B), 128, C * sizeof(float), st>>>(d_frames, a, d_nsteps, max_steps, C, M, ctx->post_pk,
+                                                                                 ctx->post_pb, lo, hi, d_mel);
+  B200_CUDA(cudaGetLastError());
+  ctx->launches++;
   API_END
 }

@@ -132,13 +132,96 @@ __global__ void aux_repeat_kernel(const float* __restrict__ aux_frames, int T, i
   }
 }
 
+// ---- fold_with_overlap (fatchord_version.py:293-340): ONE utterance's conditioning -> per-fold rows ----------------
+// Fold u covers samples [u*(target+overlap), u*(target+overlap) + target + 2*overlap); positions beyond S read as 0
+// (the reference zero-pads BOTH mels and aux after the end, :326-330).  aux is emitted per SAMPLE here (hop = 1 for the
+// generation kernels) because fold boundaries need not be hop aligned.
+// K-major layout for the grid kernel: mels_T[t][c][u], aux_T[t][o][u]
+__global__ void fold_cond_T_kernel(const float* __restrict__ mels_up /*[S][feat]*/, const float* __restrict__ aux_frames /*[T][O]*/,
+                                   int S, int hop, int feat, int O, int L, int stride, int nfold, int Bp,
+                                   float* __restrict__ mels_T /*[L][feat][Bp]*/, float* __restrict__ aux_T /*[L][O][Bp]*/) {
+  const size_t total = (size_t)L * (feat + O) * Bp;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int u = (int)(e % Bp);
+    const size_t r = e / Bp;
+    const int c = (int)(r % (feat + O));
+    const int t = (int)(r / (feat + O));
+    const long long pos = (long long)u * stride + t;
+    const bool in = u < nfold && pos < S;
+    if (c < feat) mels_T[((size_t)t * feat + c) * Bp + u] = in ? mels_up[(size_t)pos * feat + c] : 0.f;
+    else aux_T[((size_t)t * O + (c - feat)) * Bp + u] = in ? aux_frames[(size_t)(pos / hop) * O + (c - feat)] : 0.f;
+  }
+}
+// row-major layout for the utterance kernel: mels_f[u][t][c], aux_f[u][t][o]
+__global__ void fold_cond_kernel(const float* __restrict__ mels_up, const float* __restrict__ aux_frames, int S, int hop, int feat,
+                                 int O, int L, int stride, int nfold, float* __restrict__ mels_f, float* __restrict__ aux_f) {
+  const size_t total = (size_t)nfold * L * (feat + O);
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % (feat + O));
+    const size_t r = e / (feat + O);
+    const int t = (int)(r % L);
+    const int u = (int)(r / L);
+    const long long pos = (long long)u * stride + t;
+    const bool in = pos < S;
+    if (c < feat) mels_f[((size_t)u * L + t) * feat + c] = in ? mels_up[(size_t)pos * feat + c] : 0.f;
+    else aux_f[((size_t)u * L + t) * O + (c - feat)] = in ? aux_frames[(size_t)(pos / hop) * O + (c - feat)] : 0.f;
+  }
+}
+
+// xfade_and_unfold (fatchord_version.py:342-405) + the generate() epilogue (:247-258), fp64:
+// decode every fold's labels, apply the equal-power fade-in/out over `overlap` (first half of the fade-in is silence),
+// overlap-add at stride target+overlap, truncate to wave_len, 20-hop linear fade-out.
+__global__ void xfade_unfold_kernel(const int16_t* __restrict__ labels /*[nfold][L]*/, int nfold, int L, int target, int overlap,
+                                    int wave_len, int fade_len, int ncls, int mu_law, double* __restrict__ wave /*[wave_len]*/) {
+  const double mu = (double)(ncls - 1);
+  const int stride = target + overlap;
+  const int silence = overlap / 2, flen = overlap - silence;
+  const double lin_step = -1.0 / (double)(fade_len - 1);
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < wave_len; n += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    int u_hi = n / stride;                          // last fold that can start at or before n
+    if (u_hi >= nfold) u_hi = nfold - 1;
+    for (int u = u_hi; u >= 0 && u >= u_hi - 1; --u) {
+      const int t = n - u * stride;
+      if (t < 0 || t >= L) continue;
+      float yf = label_to_float((int)labels[(size_t)u * L + t], (float)(ncls - 1));
+      double y = (double)yf;
+      if (mu_law) {
+        const double a = fabs(y), sgn = (y > 0.0) - (y < 0.0);
+        y = sgn / mu * (pow(1.0 + mu, a) - 1.0);
+      }
+      // np.linspace(-1, 1, flen)[k] = -1 + k * 2/(flen-1)
+      if (t < overlap) {
+        double g = 0.0;
+        if (t >= silence) { const int k = t - silence; const double tt = (k == flen - 1) ? 1.0 : (-1.0 + k * (2.0 / (flen - 1))); g = sqrt(0.5 * (1.0 + tt)); }
+        y *= g;
+      }
+      if (t >= L - overlap) {
+        const int k2 = t - (L - overlap);
+        double g = 1.0;
+        if (k2 >= silence) { const int k = k2 - silence; const double tt = (k == flen - 1) ? 1.0 : (-1.0 + k * (2.0 / (flen - 1))); g = sqrt(0.5 * (1.0 - tt)); }
+        y *= g;
+      }
+      acc += y;
+    }
+    const int k = n - (wave_len - fade_len);
+    if (k >= 0) acc *= (k == fade_len - 1) ? 0.0 : (1.0 + (double)k * lin_step);
+    wave[n] = acc;
+  }
+}
+
 // generate() epilogue (fatchord_version.py:243-258): float64, decode_mu_law (dsp.py:98-103), truncate, 20-hop fade.
-__global__ void finish_wave_kernel(const int16_t* __restrict__ labels /*[B][S]*/, int S, int wave_len, int fade_len,
-                                   int ncls, int mu_law, double* __restrict__ wave /*[B][wave_len]*/) {
+// `utt_frames` (optional, [B]): true frame count of each row of a zero-padded ragged batch -> that row is truncated / faded at
+// ITS OWN (T_b - 1) * hop like a batch-1 run of the reference, and zero beyond.
+__global__ void finish_wave_kernel(const int16_t* __restrict__ labels /*[B][S]*/, int S, int wave_len_max, int fade_len,
+                                   int ncls, int mu_law, const int* __restrict__ utt_frames, int hop,
+                                   double* __restrict__ wave /*[B][wave_len_max]*/) {
   const int b = blockIdx.y;
   const double mu = (double)(ncls - 1);
   const double step = -1.0 / (double)(fade_len - 1);   // np.linspace(1, 0, fade_len)
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wave_len; i += gridDim.x * blockDim.x) {
+  const int wave_len = utt_frames ? min(wave_len_max, max(0, (utt_frames[b] - 1) * hop)) : wave_len_max;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wave_len_max; i += gridDim.x * blockDim.x) {
+    if (i >= wave_len) { wave[(size_t)b * wave_len_max + i] = 0.0; continue; }
     float yf = label_to_float((int)labels[(size_t)b * S + i], (float)(ncls - 1));
     double y = (double)yf;
     if (mu_law) {
@@ -148,7 +231,7 @@ __global__ void finish_wave_kernel(const int16_t* __restrict__ labels /*[B][S]*/
     }
     int k = i - (wave_len - fade_len);
     if (k >= 0) y *= (k == fade_len - 1) ? 0.0 : (1.0 + (double)k * step);
-    wave[(size_t)b * wave_len + i] = y;
+    wave[(size_t)b * wave_len_max + i] = y;
   }
 }
 

@@ -99,7 +99,7 @@ class WaveRNNEngine:
 
     def generate(self, mels, *, seed: int = 0, utterance_offset: int = 0, q=None, teacher=None,
                  return_logits: bool = False, want_wave: bool = True, mu_law: bool = True, kernel: str = 'auto',
-                 max_steps: int = 0):
+                 max_steps: int = 0, fold=None, utt_frames=None):
         """Runs the generation loop on the device.
 
         Returns dict(labels int16 [B,S] cuda, wave float64 [B,wave_len] cuda or None, logits [S,B,NC] or None).
@@ -108,12 +108,17 @@ class WaveRNNEngine:
         m = self._mel(mels)
         B, _, T = m.shape
         S = T * self.hop
-        steps = max_steps if max_steps else S
+        GB, GS = B, S                                     # rows / steps the generation kernels see
+        if fold is not None:
+            if B != 1:
+                raise ValueError('fold-with-overlap generation takes exactly one utterance')
+            GB, GS = self.fold_geometry(T, int(fold[0]), int(fold[1]))
+        steps = max_steps if max_steps else GS
         dev = self._dev()
         with torch.cuda.device(self.device):
-            labels = torch.zeros(B, S, device=dev, dtype=torch.int16)
+            labels = torch.zeros(GB, GS, device=dev, dtype=torch.int16)
             wave = None
-            if want_wave and steps == S:
+            if want_wave and steps == GS:
                 wave = torch.empty(B, (T - 1) * self.hop, device=dev, dtype=torch.float64)
             rng = Rng()
             rng.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -121,8 +126,8 @@ class WaveRNNEngine:
             qd = None
             if q is not None:
                 qd = torch.as_tensor(q).to(device=dev, dtype=torch.float32).contiguous()
-                if qd.dim() != 3 or tuple(qd.shape[1:]) != (B, self.n_classes) or qd.shape[0] < steps:
-                    raise ValueError(f'q must be [>= {steps}, {B}, {self.n_classes}], got {tuple(qd.shape)}')
+                if qd.dim() != 3 or tuple(qd.shape[1:]) != (GB, self.n_classes) or qd.shape[0] < steps:
+                    raise ValueError(f'q must be [>= {steps}, {GB}, {self.n_classes}], got {tuple(qd.shape)}')
                 rng.mode = _lib.RNG_EXT_EXPONENTIAL
                 rng.d_q = qd.data_ptr()
             else:
@@ -131,23 +136,37 @@ class WaveRNNEngine:
             opts.kernel = _lib.KERNELS[kernel]
             opts.mu_law = 1 if mu_law else 0
             opts.max_steps = int(max_steps)
+            if fold is not None:
+                opts.fold_target, opts.fold_overlap = int(fold[0]), int(fold[1])
+            uf = None
+            if utt_frames is not None:
+                uf = torch.as_tensor(utt_frames).to(device=dev, dtype=torch.int32).contiguous()
+                if tuple(uf.shape) != (B,):
+                    raise ValueError('utt_frames must be [B]')
+                opts.d_utt_frames = uf.data_ptr()
             td = None
             if teacher is not None:
                 td = torch.as_tensor(teacher).to(device=dev, dtype=torch.int16).contiguous()
-                if tuple(td.shape) != (B, S):
-                    raise ValueError('teacher must be [B, S]')
+                if tuple(td.shape) != (GB, GS):
+                    raise ValueError('teacher must be [B, S] ([n_folds, fold_len] when folding)')
                 opts.d_teacher = td.data_ptr()
             logits = None
             if return_logits:
-                logits = torch.empty(steps, B, self.n_classes, device=dev, dtype=torch.float32)
+                logits = torch.empty(steps, GB, self.n_classes, device=dev, dtype=torch.float32)
                 opts.d_logits = logits.data_ptr()
             _lib.check(self.lib.b200tts_wavernn_generate(self._h, _ptr(m), B, T, C.byref(rng), C.byref(opts),
                                                          _ptr(labels), _ptr(wave), self._stream()))
             # keep inputs alive until the stream has consumed them
-            for t in (m, qd, td):
+            for t in (m, qd, td, uf):
                 if t is not None:
                     t.record_stream(torch.cuda.current_stream(self.device))
         return dict(labels=labels, wave=wave, logits=logits, steps=steps)
+
+    def fold_geometry(self, T: int, target: int, overlap: int):
+        """(n_folds, fold_len) of fold_with_overlap for a T-frame utterance."""
+        nf, fl = C.c_int(), C.c_int()
+        _lib.check(self.lib.b200tts_wavernn_fold_geometry(int(T), self.hop, int(target), int(overlap), C.byref(nf), C.byref(fl)))
+        return nf.value, fl.value
 
     def generate_host(self, mels: np.ndarray, *, seed: int = 0, utterance_offset: int = 0, mu_law: bool = True,
                       kernel: str = 'auto', want_labels: bool = True, want_wave: bool = True):

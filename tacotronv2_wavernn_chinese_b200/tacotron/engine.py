@@ -27,7 +27,7 @@ class TacoDecoderEngine:
         if cfg:
             self.cfg.update(cfg)
         host = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()
-                if np.asarray(v).dtype.kind == 'f' and (k.startswith('decoder/') or k.startswith('memory_layer/'))}
+                if np.asarray(v).dtype.kind == 'f'}
         arr, keep = _lib.make_tensor_array(host)
         c = TacoCfg()
         for k, v in self.cfg.items():
@@ -90,6 +90,33 @@ class TacoDecoderEngine:
                 if t is not None:
                     t.record_stream(torch.cuda.current_stream(self.device))
         return dict(frames=frames, stop=stop, align=align, nsteps=nsteps)
+
+    def encode(self, ids, lengths=None):
+        """ids int [B, Tx] (padded with anything beyond lengths) -> memory [B, Tx, enc_dim] (CUDA tensor)."""
+        dev = self._dev()
+        i = torch.as_tensor(ids).to(device=dev, dtype=torch.int32).contiguous()
+        if i.dim() != 2:
+            raise ValueError('ids must be [B, Tx]')
+        B, Tx = i.shape
+        ln = torch.full((B,), Tx, dtype=torch.int32) if lengths is None else torch.as_tensor(lengths, dtype=torch.int32)
+        ln = ln.to(dev)
+        with torch.cuda.device(self.device):
+            mem = torch.zeros(B, Tx, self.cfg['enc_dim'], device=dev, dtype=torch.float32)
+            _lib.check(self.lib.b200tts_taco_encode(self._h, _ptr(i), _ptr(ln), B, Tx, _ptr(mem), self._stream()))
+            i.record_stream(torch.cuda.current_stream(self.device)); ln.record_stream(torch.cuda.current_stream(self.device))
+        return mem
+
+    def postnet(self, frames, nsteps):
+        """frames [B, max_steps, num_mels] raw decoder outputs + nsteps [B] -> mel [B, max_steps, num_mels] (clipped)."""
+        dev = self._dev()
+        f = torch.as_tensor(frames).to(device=dev, dtype=torch.float32).contiguous()
+        n = torch.as_tensor(nsteps).to(device=dev, dtype=torch.int32).contiguous()
+        B, ms, _ = f.shape
+        with torch.cuda.device(self.device):
+            mel = torch.zeros_like(f)
+            _lib.check(self.lib.b200tts_taco_postnet(self._h, _ptr(f), _ptr(n), B, ms, _ptr(mel), self._stream()))
+            f.record_stream(torch.cuda.current_stream(self.device)); n.record_stream(torch.cuda.current_stream(self.device))
+        return mel
 
     def philox_masks(self, seed, utterance_offset, B, steps):
         with torch.cuda.device(self.device):

@@ -152,9 +152,6 @@ class WaveRNN(nn.Module):
         `return_all=True`, which gives [B, wave_len].  `seed` fixes the Philox sampling stream (default: derived
         from torch.initial_seed() and a per-model call counter, so torch.manual_seed(k) reproduces a run).
         """
-        if batched:
-            raise NotImplementedError('fold-with-overlap batched generation (:293-405) is not on the B200 path yet; '
-                                      'the reference CLI forces batched=False as well (wavernn_gen.py:77)')
         self.eval()
         start = time.time()
         mu_law = mu_law if self.mode == 'RAW' else False
@@ -168,7 +165,9 @@ class WaveRNN(nn.Module):
         if seed is None:
             seed = (int(torch.initial_seed()) * 1000003 + self._gen_calls) & 0xFFFFFFFFFFFFFFFF
         self._gen_calls += 1
-        out = eng.generate(m, seed=seed, mu_law=bool(mu_law), kernel=kernel)
+        if batched and m.shape[0] != 1:
+            raise ValueError('batched (fold-with-overlap) generation folds ONE utterance (fatchord_version.py:293-340)')
+        out = eng.generate(m, seed=seed, mu_law=bool(mu_law), kernel=kernel, fold=(target, overlap) if batched else None)
         wave = out['wave'].cpu().numpy()                       # [B, wave_len] float64 (synchronises)
         self.last_labels = out['labels']
         self.last_gen_seconds = time.time() - start

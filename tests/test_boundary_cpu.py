@@ -51,7 +51,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(L.WaveRNNCfg) == 14 * 4
     assert ctypes.sizeof(L.Tensor) == 8 + 8 + 8 + 32
     assert ctypes.sizeof(L.Rng) == 32
-    assert ctypes.sizeof(L.GenOpts) == 32
+    assert ctypes.sizeof(L.GenOpts) == 48
 
 
 def test_hparams_singleton_contract(tmp_path):
@@ -138,8 +138,6 @@ def test_model_keys_and_cpu_refusal():
     assert set(sd) == set(m.state_dict())
     for k, v in m.state_dict().items():
         assert tuple(v.shape) == sd[k].shape, k
-    with pytest.raises(NotImplementedError):
-        m.generate(torch.zeros(1, 80, 30), None, True, 11000, 550, True)
     with pytest.raises(ValueError):
         m.generate(torch.zeros(1, 80, 20), None, False, 11000, 550, True) if torch.cuda.is_available() else (_ for _ in ()).throw(ValueError())
     if not torch.cuda.is_available():

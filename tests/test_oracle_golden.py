@@ -77,6 +77,20 @@ def test_generate_config1_shape_labels(ckpt_state_dict):
     np.testing.assert_allclose(r['wave'][0], g['wave0'], rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize('case', ['wavernn_synth_batched_T30', 'wavernn_ckpt_batched_T30'])
+def test_batched_generate_matches_reference(case, request):
+    """generate(batched=True): fold_with_overlap + xfade_and_unfold (fatchord_version.py:293-405) vs the reference's own run."""
+    g = _load(case)
+    p = _params('wavernn_synth' if 'synth' in case else 'ckpt', request.getfixturevalue('ckpt_state_dict') if 'ckpt' in case else None)
+    T, target, overlap = int(g['T']), int(g['target']), int(g['overlap'])
+    mel = synth.synth_mels(int(g['mel_seed']), 1, T)
+    nf, L = g['labels'].shape
+    q = synth.synth_exponential_noise(int(g['noise_seed']), L, nf)
+    r = wo.generate_batched(p, mel, target, overlap, q=q)
+    assert np.array_equal(r['labels'], g['labels'])
+    np.testing.assert_allclose(r['wave'], g['wave'], rtol=0, atol=1e-12)
+
+
 def test_finish_wave_requires_21_frames():
     with pytest.raises(ValueError):
         wo.finish_wave(np.zeros((1, 20 * 275), dtype=np.int16), 1024, 19 * 275, 275)

@@ -192,6 +192,40 @@ def test_kernels_agree_full_size(torch_cuda):
     assert agree.mean() >= 0.8, f'only {agree.mean():.2f} of utterances agree between kernels'
 
 
+@pytest.mark.parametrize('kernel', KERNELS)
+@pytest.mark.parametrize('name', ['wavernn_synth_batched_T30', 'wavernn_ckpt_batched_T30'])
+def test_fold_with_overlap_vs_reference_golden(torch_cuda, name, kernel):
+    """--batched mode (fold_with_overlap + xfade_and_unfold, fatchord_version.py:293-405) against the reference's own
+    generate(batched=True) under shared noise; the ckpt case uses target/overlap that are NOT hop aligned."""
+    g = _golden(name)
+    eng, p = engine_for(_case_of(name))
+    T, target, overlap = int(g['T']), int(g['target']), int(g['overlap'])
+    mel = synth.synth_mels(int(g['mel_seed']), 1, T)
+    nf, L = g['labels'].shape
+    assert eng.fold_geometry(T, target, overlap) == (nf, L)
+    q = synth.synth_exponential_noise(int(g['noise_seed']), L, nf)
+    out = eng.generate(mel, q=q, kernel=kernel, fold=(target, overlap))
+    lab = out['labels'].cpu().numpy()
+    assert lab.shape == (nf, L)
+    for b in range(nf):
+        mism = np.nonzero(lab[b] != g['labels'][b])[0]
+        if mism.size:     # accepted only when the race (l - log q) has a genuine near-tie at that step (teacher-forced oracle)
+            t = int(mism[0])
+            r = wo.generate_batched(p, mel, target, overlap, q=q, teacher=g['labels'], keep_logits=(t,), max_steps=t + 1)
+            key = r['logits'][t][b].astype(np.float64) - np.log(q[t, b].astype(np.float64))
+            top = np.sort(key)[-2:]
+            assert t > L // 4 and (top[1] - top[0]) < 1e-3 * max(1.0, abs(top[1])), \
+                f'fold {b} diverged from the reference at step {t} without a sampling near-tie (gap {top[1] - top[0]:.3e})'
+    if np.array_equal(lab, g['labels']):
+        np.testing.assert_allclose(out['wave'].cpu().numpy()[0], g['wave'], rtol=0, atol=1e-12)
+    # the unfold/cross-fade epilogue on the reference's own labels (independent of sampling)
+    ref = wo.xfade_and_unfold(wo.decode_mu_law(wo.label_to_float(lab, 1024).astype(np.float64), 1024), target, overlap)
+    wl = (T - 1) * 275
+    ref = ref[:wl].copy()
+    ref[-20 * 275:] *= np.linspace(1, 0, 20 * 275)
+    np.testing.assert_allclose(out['wave'].cpu().numpy()[0], ref, rtol=0, atol=1e-12)
+
+
 def test_host_entry_point_equals_device_path(torch_cuda):
     eng, _ = engine_for('synth5')
     mels = synth.synth_mels(9, 2, 22)
@@ -255,5 +289,7 @@ def test_dropin_model_generate(torch_cuda, tmp_path):
     eng, p = engine_for('synth5')
     lab = m.last_labels.cpu().numpy()
     np.testing.assert_allclose(w1, wo.finish_wave(lab, 1024, 22 * 275, 275)[0], rtol=0, atol=1e-12)
+    wb = m.generate(torch.as_tensor(synth.synth_mels(4, 1, 40)), None, True, 2750, 550, True)     # --batched
+    assert wb.shape == (39 * 275,) and np.isfinite(wb).all() and np.all(wb[:275] == 0.0)            # fade-in starts silent
     up, aux = m.upsample(torch.as_tensor(_padded(mel.numpy())))
     assert tuple(up.shape) == (1, 23 * 275, 80) and tuple(aux.shape) == (1, 23 * 275, 128)

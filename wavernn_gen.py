@@ -68,7 +68,9 @@ def main(argv=None):
     hp.configure(args.hp_file)
     target = hp.voc_target if args.target is None else args.target
     overlap = hp.voc_overlap if args.overlap is None else args.overlap
-    batched = False          # the reference ignores --batched/-b and always runs unbatched (wavernn_gen.py:77)
+    # the reference parses --batched/-b but then forces False (wavernn_gen.py:77); here the flag is honoured and the
+    # default stays hp.voc_gen_batched (False)
+    batched = hp.voc_gen_batched if args.batched is None else args.batched
     if args.force_cpu:
         raise SystemExit('--force_cpu: this build runs the generation loop on sm_100a only; there is no CPU fallback')
     if not torch.cuda.is_available():
