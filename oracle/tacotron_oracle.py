@@ -157,13 +157,15 @@ def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, 
                 pos_rec = pos_rec + 1
             else:
                 pos_rec = 1
-            if not pos_rec < 9:
+            if not pos_rec < 10:                                                             # :191-195
                 new_max, pos_rec = new_max + 1, 1
             idx = np.arange(Tx)
             keep = (idx >= new_max - 2) & (idx < new_max + 3)
             al = np.where(keep, al, F32(0)).astype(F32)
             peak = idx == min(max(new_max, 0), Tx - 1)
-            al = np.where(peak & (idx < new_max + 1), F32(0.1) + al.sum(dtype=F32) * F32(2.0), al).astype(F32)
+            tot = al.sum(dtype=F32)
+            tot = F32(1.0) if tot < F32(1e-10) else tot                                      # :209-213
+            al = np.where(peak & (idx < new_max + 1), tot * F32(2.0), al).astype(F32)        # :215
         max_att = new_max
         al = (al / al.sum(dtype=F32)).astype(F32)                                            # :220
         ctx = (al[None, :] @ memory).astype(F32)                                             # :222

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kTacoThreads, 1) taco_decoder_kernel(TacoWeigh
         int nm = (am <= s_max) ? s_max : s_max + 1;
         if (s_pos < 5 && 2 < nm) nm = s_max;
         int pr = (nm == s_max) ? s_pos + 1 : 1;
-        if (!(pr < 9)) { nm = nm + 1; pr = 1; }
+        if (!(pr < 10)) { nm = nm + 1; pr = 1; }                               // :191-195
         s_max = nm; s_pos = pr;
       }
       __syncthreads();
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kTacoThreads, 1) taco_decoder_kernel(TacoWeigh
         ws += al[t];
       }
       const float wsum = block_sum(ws, red);
-      if (tid == 0) { const int pk = min(max(nm, 0), Tx - 1); al[pk] = 0.1f + wsum * 2.0f; }
+      if (tid == 0) { const int pk = min(max(nm, 0), Tx - 1); al[pk] = (wsum < 1e-10f ? 1.0f : wsum) * 2.0f; }   // :209-215
       __syncthreads();
       fs = 0.f;
       for (int t = tid; t < Tx; t += kTacoThreads) fs += al[t];
