@@ -360,10 +360,10 @@ extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b
     g.ok = (R == F) && (R % kUPC == 0) && (NC == g.ncta * kCPC) && (FEAT % 4 == 0) && (g.ncta <= ctx->sm_count);
     int off = 0;
     auto take = [&](int n) { int o = off; off += (n + 3) & ~3; return o; };
-    g.oI_w = take(kUPC * g.ldC); g.oI_x = take(kUPC); g.oI_b = take(kUPC);
-    g.oih1 = take(3 * kUPC * R); g.ohh1 = take(3 * kUPC * R); g.oih2 = take(3 * kUPC * g.ldX); g.ohh2 = take(3 * kUPC * R);
+    g.oA_w = take(16 * g.ldC); g.oA_x = take(16); g.oA_b = take(16);
+    g.ohh1 = take(3 * kUPC * R); g.oih2 = take(3 * kUPC * g.ldX); g.ohh2 = take(3 * kUPC * R);
     g.ofc1 = take(kUPC * g.ldX); g.ofc2 = take(kUPC * g.ldF); g.ofc3 = take(kCPC * F);
-    g.obih1 = take(3 * kUPC); g.obhh1 = take(3 * kUPC); g.obih2 = take(3 * kUPC); g.obhh2 = take(3 * kUPC);
+    g.obhh1 = take(3 * kUPC); g.obih2 = take(3 * kUPC); g.obhh2 = take(3 * kUPC);
     g.obfc1 = take(kUPC); g.obfc2 = take(kUPC); g.obfc3 = take(kCPC);
     g.blob = off;
     size_t smem_need = ((size_t)g.blob + (size_t)MapTraits<4, 2, 1>::kScratchFloats) * sizeof(float) + 2048;
@@ -372,26 +372,42 @@ extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b
     if (!ctx->coop) g.ok = 0;
     if (g.ok) {
       std::vector<float> hb((size_t)g.ncta * g.blob, 0.f);
+      std::vector<double> fold_acc(1 + g.ldC);
       const float* P = pk.h.data();
       for (int cta = 0; cta < g.ncta; ++cta) {
         float* b = &hb[(size_t)cta * g.blob];
         for (int j = 0; j < kUPC; ++j) {
           const int row = cta * kUPC + j;
           const float* src = P + oI + (size_t)row * ldI;          // [x | feat | aux] padded
-          b[g.oI_x + j] = src[0];
-          std::memcpy(b + g.oI_w + (size_t)j * g.ldC, src + 1, sizeof(float) * g.ldC);
-          b[g.oI_b + j] = P[oIb + row];
+          b[g.oA_x + j] = src[0];
+          std::memcpy(b + g.oA_w + (size_t)j * g.ldC, src + 1, sizeof(float) * g.ldC);
+          b[g.oA_b + j] = P[oIb + row];
           std::memcpy(b + g.ofc1 + (size_t)j * g.ldX, P + o_fc1 + (size_t)row * g.ldX, sizeof(float) * g.ldX);
           std::memcpy(b + g.ofc2 + (size_t)j * g.ldF, P + o_fc2 + (size_t)row * g.ldF, sizeof(float) * g.ldF);
           b[g.obfc1 + j] = P[o_fc1b + row];
           b[g.obfc2 + j] = P[o_fc2b + row];
           for (int gate = 0; gate < 3; ++gate) {
             const int srow = gate * R + row, drow = gate * kUPC + j;
-            std::memcpy(b + g.oih1 + (size_t)drow * R, P + o_ih1 + (size_t)srow * R, sizeof(float) * R);
+            // folded input projection of GRU 1: row srow of W_ih1.W_I (x column | cond columns) and W_ih1.b_I + b_ih1, in double
+            {
+              const float* wr = P + o_ih1 + (size_t)srow * R;
+              double bacc = (double)P[o_bih1 + srow];
+              std::vector<double>& accv = fold_acc;
+              std::fill(accv.begin(), accv.end(), 0.0);
+              for (int k = 0; k < R; ++k) {
+                const double wk = (double)wr[k];
+                const float* irow = P + oI + (size_t)k * ldI;
+                for (int col = 0; col < 1 + g.ldC; ++col) accv[col] += wk * (double)irow[col];
+                bacc += wk * (double)P[oIb + k];
+              }
+              b[g.oA_x + 4 + drow] = (float)accv[0];
+              for (int col = 0; col < g.ldC; ++col) b[g.oA_w + (size_t)(4 + drow) * g.ldC + col] = (float)accv[1 + col];
+              b[g.oA_b + 4 + drow] = (float)bacc;
+            }
             std::memcpy(b + g.ohh1 + (size_t)drow * R, P + o_hh1 + (size_t)srow * R, sizeof(float) * R);
             std::memcpy(b + g.oih2 + (size_t)drow * g.ldX, P + o_ih2 + (size_t)srow * g.ldX, sizeof(float) * g.ldX);
             std::memcpy(b + g.ohh2 + (size_t)drow * R, P + o_hh2 + (size_t)srow * R, sizeof(float) * R);
-            b[g.obih1 + drow] = P[o_bih1 + srow]; b[g.obhh1 + drow] = P[o_bhh1 + srow];
+            b[g.obhh1 + drow] = P[o_bhh1 + srow];
             b[g.obih2 + drow] = P[o_bih2 + srow]; b[g.obhh2 + drow] = P[o_bhh2 + srow];
           }
         }
@@ -597,7 +613,7 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   }
   // activations + sync words, zero-initialised (h1 = h2 = 0, fatchord_version.py:194-195)
   const size_t RB = (size_t)g.R * Bp;
-  const size_t act_floats = 9 * RB;
+  const size_t act_floats = 8 * RB;
   const size_t sync_bytes = 2 * (size_t)Bp * sizeof(unsigned long long) + 512;
   ctx->grid_scratch.ensure(act_floats * sizeof(float));
   ctx->grid_sync.ensure(sync_bytes);
@@ -606,8 +622,8 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   float* base = ctx->grid_scratch.as<float>();
   GridArgs a{};
   a.wblob = ctx->grid_blob.as<float>();
-  a.Iout = base; a.h1 = base + RB; a.h2 = base + 3 * RB; a.x1 = base + 5 * RB; a.x2 = base + 6 * RB;
-  a.f1 = base + 7 * RB; a.f2 = base + 8 * RB;
+  a.h1 = base; a.h2 = base + 2 * RB; a.x1 = base + 4 * RB; a.x2 = base + 5 * RB;
+  a.f1 = base + 6 * RB; a.f2 = base + 7 * RB;
   a.best = ctx->grid_sync.as<unsigned long long>();
   a.barrier = reinterpret_cast<unsigned int*>(ctx->grid_sync.as<char>() + 2 * (size_t)Bp * sizeof(unsigned long long));
   a.error = reinterpret_cast<int*>(a.barrier + 96);

@@ -5,11 +5,13 @@
 // that produce hidden units / fc rows [4c, 4c+4) and classes [8c, 8c+8) (136 KB), and all B utterances advance in
 // lock step.  Per step each layer is a skinny GEMM  out[B, rows_c] = act[B, K] . W_c[rows_c, K]^T : the activations
 // ([K][Bp] fp32, K-major, L2-resident, 2 KB per utterance per layer) are the only thing that moves; weights never do.
-// Layers are separated by a grid-wide barrier (monotonic counter in L2, release/acquire).
+// Phases are separated by a grid-wide barrier (monotonic counter in L2, release/acquire).
 //
 // Replaces the hot loop of WaveRNN.generate, reference wavernn/models/fatchord_version.py:201-237, phase by phase:
-//   P0  I        (:208-209)  x|m_t|a1 -> Iout                        4 rows  x 113
-//   P1  GRU rnn1 (:210,:212) Iout,h1 -> h1', x1 = Iout + h1'         24 rows x 512
+//   P01 I (:208-209) + GRU rnn1 (:210,:212): the I layer is FOLDED into the GRU's input projection,
+//       W_ih1.(W_I.[x|m_t|a1] + b_I) + b_ih1 = (W_ih1.W_I).[x|m_t|a1] + (W_ih1.b_I + b_ih1)   (product formed in fp64 on the
+//       host), so one phase computes Iout rows (4 x 113), gi (12 x 113), gh (12 x 512), h1' and x1 = Iout + h1'.
+//       This removes a grid barrier, 14 % of the MACs and the Iout round trip through L2.
 //   P2  GRU rnn2 (:213-216)  x1|a2,h2 -> h2', x2 = x1 + h2'          12 x 544 + 12 x 512
 //   P3  fc1+relu (:217-218)  x2|a3 -> f1                              4 rows x 544
 //   P4  fc2+relu (:220-221)  f1|a4 -> f2                              4 rows x 544
@@ -39,17 +41,16 @@ struct GridModel {        // layout of one CTA's weight blob (offsets in floats,
   int ldC;                // feat + aux   (cond columns of I, multiple of 4)
   int ldX;                // R + aux
   int ldF;                // F + aux
-  int oI_w, oI_x, oI_b;                            // [4][ldC], [4], [4]
-  int oih1, ohh1, oih2, ohh2;                      // [12][R], [12][R], [12][ldX], [12][R]   row = gate*4 + unit
+  int oA_w, oA_x, oA_b;                            // [16][ldC], [16], [16]: rows 0-3 = I, rows 4-15 = W_ih1.W_I (gate*4 + unit)
+  int ohh1, oih2, ohh2;                            // [12][R], [12][ldX], [12][R]   row = gate*4 + unit
   int ofc1, ofc2, ofc3;                            // [4][ldX], [4][ldF], [8][F]
-  int obih1, obhh1, obih2, obhh2, obfc1, obfc2, obfc3;
+  int obhh1, obih2, obhh2, obfc1, obfc2, obfc3;
   int blob;                                        // floats per CTA
   int ok;                                          // model fits this kernel
 };
 
 struct GridArgs {
   const float* wblob;          // [ncta][blob]
-  float* Iout;                 // [R][Bp]
   float* h1;                   // [2][R][Bp]
   float* h2;                   // [2][R][Bp]
   float* x1;                   // [R][Bp]
@@ -185,41 +186,32 @@ __device__ __forceinline__ void wide_accumulate_pd(float (&acc)[RT][U], const fl
   const float* p = act + (size_t)(4 * lo) * Bp + u0;
   const size_t step = (size_t)4 * Bp;
   const int n = hi - lo;
+  const int nmain = n - n % (2 * PD);          // every shape of this model gives n % 4 == 0; the tail loop is only a safety net
   float c[PD][4][U], nb[PD][4][U];
-  int i = 0;
-  if (n >= PD) {
+  // ONE copy of the unrolled body (2*PD blocks of 4*RT*U FMAs): the look-ahead loads of the last trip are predicated
+  // instead of peeling prologue / epilogue variants (the fully peeled version made the kernel 288 KB of SASS).
+  if (nmain > 0) {
 #pragma unroll
     for (int j = 0; j < PD; ++j) wide_ld4<U>(c[j], p + j * step, Bp);
     p += PD * step;
-    for (; i + 3 * PD <= n; i += 2 * PD) {
+#pragma unroll 1
+    for (int i = 0; i < nmain; i += 2 * PD) {
 #pragma unroll
       for (int j = 0; j < PD; ++j) wide_ld4<U>(nb[j], p + j * step, Bp);
       p += PD * step;
 #pragma unroll
       for (int j = 0; j < PD; ++j) wide_fma4<U, RT>(acc, W4, ldw4, i + j, c[j]);
+      if (i + 2 * PD < nmain) {
 #pragma unroll
-      for (int j = 0; j < PD; ++j) wide_ld4<U>(c[j], p + j * step, Bp);
-      p += PD * step;
-#pragma unroll
-      for (int j = 0; j < PD; ++j) wide_fma4<U, RT>(acc, W4, ldw4, i + PD + j, nb[j]);
-    }
-    if (i + 2 * PD <= n) {
-#pragma unroll
-      for (int j = 0; j < PD; ++j) wide_ld4<U>(nb[j], p + j * step, Bp);
-      p += PD * step;
-#pragma unroll
-      for (int j = 0; j < PD; ++j) wide_fma4<U, RT>(acc, W4, ldw4, i + j, c[j]);
+        for (int j = 0; j < PD; ++j) wide_ld4<U>(c[j], p + j * step, Bp);
+        p += PD * step;
+      }
 #pragma unroll
       for (int j = 0; j < PD; ++j) wide_fma4<U, RT>(acc, W4, ldw4, i + PD + j, nb[j]);
-      i += 2 * PD;
-    } else {
-#pragma unroll
-      for (int j = 0; j < PD; ++j) wide_fma4<U, RT>(acc, W4, ldw4, i + j, c[j]);
-      i += PD;
     }
   }
 #pragma unroll 1
-  for (; i < n; ++i) {
+  for (int i = nmain; i < n; ++i) {
     wide_ld4<U>(c[0], p, Bp); p += step;
     wide_fma4<U, RT>(acc, W4, ldw4, i, c[0]);
   }
@@ -252,10 +244,19 @@ __device__ __forceinline__ void wide_partials(float* part, const Gemm& g0, const
   int N4 = G.seg[0].n4 + (G.nseg > 1 ? G.seg[1].n4 : 0);
   const int lo = N4 * ks / KS, hi = N4 * (ks + 1) / KS;
   int col = 0;
+  if constexpr (NG == 2) {                        // the big 2-GEMM phase: segments unrolled (measured faster for P2)
 #pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    if (s < G.nseg) {
-      int a = max(lo, col), b = min(hi, col + G.seg[s].n4);
+    for (int s = 0; s < 2; ++s) {
+      if (s < G.nseg) {
+        const int a = max(lo, col), b = min(hi, col + G.seg[s].n4);
+        if (a < b) wide_accumulate<U, RT>(acc, G.W, G.ldw, col, G.seg[s].act, Bp, tile_base + ul, a - col, b - col);
+        col += G.seg[s].n4;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int s = 0; s < G.nseg; ++s) {            // runtime loop: one copy of the GEMM body per call site
+      const int a = max(lo, col), b = min(hi, col + G.seg[s].n4);
       if (a < b) wide_accumulate<U, RT>(acc, G.W, G.ldw, col, G.seg[s].act, Bp, tile_base + ul, a - col, b - col);
       col += G.seg[s].n4;
     }
@@ -263,6 +264,30 @@ __device__ __forceinline__ void wide_partials(float* part, const Gemm& g0, const
   float* dst = part + (size_t)((g * KS + ks) * RT) * BT + ul;
 #pragma unroll
   for (int r = 0; r < RT; ++r) ActLoad<U>::st(dst + r * BT, acc[r]);
+}
+
+// P01 cond rows (K = feat + aux = 112 is tiny): no k split -- warps = UW utterance warps x RG row groups, each row group
+// takes 16/RG of the 16 rows over all columns; results go straight to resA[row*BT + ul].
+template <int NWG, int U, int UW>
+__device__ __forceinline__ void wide_cond_rows(float* resA, const float* __restrict__ Wsm, int ldC, const Seg& s0, const Seg& s1,
+                                               int tile_base, int Bp, int warp, int lane) {
+  constexpr int RG = NWG / UW, RTA = 16 / RG, BT = 32 * U * UW;
+  static_assert(RG * RTA == 16, "row groups must tile the 16 cond rows");
+  const int uw = warp % UW, rg = warp / UW;
+  const int ul = uw * 32 * U + lane * U;
+  float acc[RTA][U];
+#pragma unroll
+  for (int r = 0; r < RTA; ++r)
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[r][u] = 0.f;
+  const float* W = Wsm + rg * RTA * ldC;
+#pragma unroll 1
+  for (int s = 0; s < 2; ++s) {
+    const Seg& sg = s ? s1 : s0;
+    wide_accumulate<U, RTA>(acc, W, ldC, s ? s0.n4 : 0, sg.act, Bp, tile_base + ul, 0, sg.n4);
+  }
+#pragma unroll
+  for (int r = 0; r < RTA; ++r) ActLoad<U>::st(resA + (size_t)(rg * RTA + r) * BT + ul, acc[r]);
 }
 
 // Narrow mapping (Bp == G <= 8): the whole activation vector of the phase is first staged into shared memory by all
@@ -331,7 +356,8 @@ template <int U, int UW, int GROUPS> struct MapTraits {
   static constexpr int BT = 32 * U * UW;                                   // utterances per group tile
   static constexpr int KS1 = NWG / UW;                                     // k slices of a 1-GEMM phase
   static constexpr int KS2 = NWG / (2 * UW);                               // ... of a 2-GEMM phase
-  static constexpr int kGroupScratch = (NWG / UW) * 3 * kUPC * BT;         // partial sums of the largest phase, per group
+  static constexpr int kPartFloats = (NWG / UW) * 3 * kUPC * BT;           // k-split partial sums of the largest GEMM phase
+  static constexpr int kGroupScratch = kPartFloats + 16 * BT;              // + the un-split cond rows of P01, per group
   static constexpr int kScratchFloats = GROUPS * kGroupScratch;
   static_assert(KS2 >= 1 && KS2 * 2 * UW == NWG, "group warps must factor as 2 x UW x KS2");
 };
@@ -342,7 +368,8 @@ template <int G> struct MapTraits<0, G, 1> {
   static constexpr int BT = G;
   static constexpr int KS1 = 1;
   static constexpr int KS2 = 1;
-  static constexpr int kGroupScratch = 640 * G + 512 * G + 2 * 3 * kUPC * G + 64;   // staged act A | act B | row results
+  static constexpr int kPartFloats = 0;
+  static constexpr int kGroupScratch = 640 * G + 512 * G + 32 * G + 64;   // staged act A | act B | row results (16 + 12 rows)
   static constexpr int kScratchFloats = kGroupScratch;
 };
 
@@ -388,8 +415,6 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
     for (int i = threadIdx.x; i < M.blob / 4; i += GROUPS * NT) dst[i] = __ldg(src + i);
   }
   __syncthreads();
-  const float* bI = Wb + M.oI_b;
-  const float* wIx = Wb + M.oI_x;
   unsigned int nbar = 0;
   const unsigned int ncta = gridDim.x;
   const size_t RB = (size_t)R * Bp;
@@ -419,7 +444,7 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
     const float* h2c = A.h2 + cur * RB;
     float* h2n = A.h2 + (cur ^ 1) * RB;
 
-    // ================= P0: read back the previous step's winner, then the I layer =================
+    // ================= P01: read back the previous step's winner; I layer folded into GRU 1 =================
     for (int tb = tb_lo; tb < tb_hi; tb += BT) {
       for (int ul = tid; ul < BT; ul += NT) {
         const int u = tb + ul;
@@ -434,67 +459,48 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
         xs[ul] = x;
       }
       const float* melT = A.mels_T + (size_t)t * M.FEAT * Bp;
+      const float* rA;        // [16][BT]: cond part of the 4 I rows and the 12 folded gi rows
+      const float* rB;        // gh partial sums (k slices) / rows
       if constexpr (MT::kWide) {
-        Gemm g{};
-        g.W = Wb + M.oI_w; g.ldw = M.ldC; g.nseg = 2;
-        g.seg[0] = Seg{melT, M.FEAT / 4};
-        g.seg[1] = Seg{auxT, AUX / 4};
-        wide_partials<NWG, U, UW, kUPC, 1>(part, g, g, tb, Bp, warp, lane);
+        float* resA = part + MT::kPartFloats;
+        wide_cond_rows<NWG, U, UW>(resA, Wb + M.oA_w, M.ldC, Seg{melT, M.FEAT / 4}, Seg{auxT, AUX / 4}, tb, Bp, warp, lane);
+        Gemm gh{};
+        gh.W = Wb + M.ohh1; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h1c, R / 4};
+        wide_partials<NWG, U, UW, 3 * kUPC, 1>(part, gh, gh, tb, Bp, warp, lane);
+        rA = resA; rB = part;
       } else {
         stage_rows<NT>(stA, melT, M.FEAT * G, tid);
         stage_rows<NT>(stA + M.FEAT * G, auxT, AUX * G, tid);
+        stage_rows<NT>(stB, h1c, R * G, tid);
         group_sync<GROUPS, NT>(grp);
-        narrow_rows<G, 1>(nout, 0, Wb + M.oI_w, M.ldC, stA, M.ldC / 4, kUPC, 0, NWG, warp, lane);
+        narrow_rows<G, 4>(nout, 0, Wb + M.oA_w, M.ldC, stA, M.ldC / 4, 16, 0, NWG / 2, warp, lane);
+        narrow_rows<G, 3>(nout + 16 * G, 0, Wb + M.ohh1, R, stB, R / 4, 3 * kUPC, NWG / 2, NWG / 2, warp, lane);
+        rA = nout; rB = nout + 16 * G;
       }
       group_sync<GROUPS, NT>(grp);
+      const float* wAx = Wb + M.oA_x; const float* bA = Wb + M.oA_b; const float* bhh = Wb + M.obhh1;
       for (int idx = tid; idx < BT * kUPC; idx += NT) {
         const int ul = idx % BT, j = idx / BT;
-        float v = part_sum<KS1, kUPC, BT>(res, 0, j, ul);
-        v = fmaf(wIx[j], xs[ul], v) + bI[j];
-        A.Iout[(size_t)(c * kUPC + j) * Bp + tb + ul] = v;
+        const size_t o = (size_t)(c * kUPC + j) * Bp + tb + ul;
+        const float x = xs[ul];
+        float hold;
+        if constexpr (MT::kWide) hold = __ldcg(h1c + o);
+        else hold = stB[(c * kUPC + j) * G + ul];
+        const float iout = fmaf(wAx[j], x, rA[(size_t)j * BT + ul]) + bA[j];
+        const float gir = fmaf(wAx[4 + j], x, rA[(size_t)(4 + j) * BT + ul]) + bA[4 + j];
+        const float giz = fmaf(wAx[4 + kUPC + j], x, rA[(size_t)(4 + kUPC + j) * BT + ul]) + bA[4 + kUPC + j];
+        const float gin = fmaf(wAx[4 + 2 * kUPC + j], x, rA[(size_t)(4 + 2 * kUPC + j) * BT + ul]) + bA[4 + 2 * kUPC + j];
+        float h = gru_update(gir, giz, gin, part_sum<KS1, 3 * kUPC, BT>(rB, 0, j, ul) + bhh[j],
+                             part_sum<KS1, 3 * kUPC, BT>(rB, 0, kUPC + j, ul) + bhh[kUPC + j],
+                             part_sum<KS1, 3 * kUPC, BT>(rB, 0, 2 * kUPC + j, ul) + bhh[2 * kUPC + j], hold);
+        h1n[o] = h;
+        A.x1[o] = iout + h;
       }
       if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(0);
     if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
     PROF_MARK(1);
-
-    // ================= P1: GRU 1 =================
-    for (int tb = tb_lo; tb < tb_hi; tb += BT) {
-      if constexpr (MT::kWide) {
-        Gemm gi{}, gh{};
-        gi.W = Wb + M.oih1; gi.ldw = R; gi.nseg = 1; gi.seg[0] = Seg{A.Iout, R / 4};
-        gh.W = Wb + M.ohh1; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h1c, R / 4};
-        wide_partials<NWG, U, UW, 3 * kUPC, 2>(part, gi, gh, tb, Bp, warp, lane);
-      } else {
-        stage_rows<NT>(stA, A.Iout, R * G, tid);
-        stage_rows<NT>(stB, h1c, R * G, tid);
-        group_sync<GROUPS, NT>(grp);
-        narrow_rows<G, 3>(nout, 0, Wb + M.oih1, R, stA, R / 4, 3 * kUPC, 0, NWG / 2, warp, lane);
-        narrow_rows<G, 3>(nout, 1, Wb + M.ohh1, R, stB, R / 4, 3 * kUPC, NWG / 2, NWG / 2, warp, lane);
-      }
-      group_sync<GROUPS, NT>(grp);
-      const float* bih = Wb + M.obih1; const float* bhh = Wb + M.obhh1;
-      for (int idx = tid; idx < BT * kUPC; idx += NT) {
-        const int ul = idx % BT, j = idx / BT;
-        const size_t o = (size_t)(c * kUPC + j) * Bp + tb + ul;
-        float hold, resid;
-        if constexpr (MT::kWide) { hold = __ldcg(h1c + o); resid = __ldcg(A.Iout + o); }
-        else { hold = stB[(c * kUPC + j) * G + ul]; resid = stA[(c * kUPC + j) * G + ul]; }
-        float h = gru_update(part_sum<KS2, 3 * kUPC, BT>(res, 0, j, ul) + bih[j],
-                             part_sum<KS2, 3 * kUPC, BT>(res, 0, kUPC + j, ul) + bih[kUPC + j],
-                             part_sum<KS2, 3 * kUPC, BT>(res, 0, 2 * kUPC + j, ul) + bih[2 * kUPC + j],
-                             part_sum<KS2, 3 * kUPC, BT>(res, 1, j, ul) + bhh[j],
-                             part_sum<KS2, 3 * kUPC, BT>(res, 1, kUPC + j, ul) + bhh[kUPC + j],
-                             part_sum<KS2, 3 * kUPC, BT>(res, 1, 2 * kUPC + j, ul) + bhh[2 * kUPC + j], hold);
-        h1n[o] = h;
-        A.x1[o] = resid + h;
-      }
-      if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
-    }
-    PROF_MARK(2);
-    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
-    PROF_MARK(3);
 
     // ================= P2: GRU 2 =================
     for (int tb = tb_lo; tb < tb_hi; tb += BT) {
