@@ -93,21 +93,48 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
 
 
+_BEST_THREADS = None
+
+
+def _pick_threads(wo, p, mels):
+    """The matvecs of one utterance are tiny (1536 x 512): more BLAS threads than ~8-16 only adds contention.  Probe a
+    few pool sizes on 150 steps each and keep the fastest -- "all the host threads it can USE"."""
+    global _BEST_THREADS
+    if _BEST_THREADS is not None:
+        return _BEST_THREADS
+    ncpu = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        _BEST_THREADS = ncpu
+        return ncpu
+    best, best_rate = 1, 0.0
+    for nt in sorted({1, 4, 8, 16, 32, ncpu} & set(range(1, ncpu + 1))):
+        with threadpool_limits(limits=nt):
+            wo.generate(p, mels, max_steps=20, seed=0)
+            r = wo.generate(p, mels, max_steps=150, seed=0)
+        rate = 150 / r['seconds']
+        if rate > best_rate:
+            best, best_rate = nt, rate
+    _BEST_THREADS = best
+    return best
+
+
 def cpu_oracle_rate(frames, max_seconds=25.0):
     """The reference algorithm (numpy oracle port, oracle/wavernn_oracle.py) on the host: one utterance, as many of
-    its T*hop steps as fit the time bound.  Returns (samples/s, steps run, threads)."""
+    its T*hop steps as fit the time bound.  Returns (samples/s, steps run, threads used)."""
     from oracle import wavernn_oracle as wo
     from tacotronv2_wavernn_chinese_b200 import synth
     import contextlib
-    threads = os.cpu_count() or 1
+    p = wo.as_params(synth.synth_state_dict(0))
+    mels = synth.synth_mels(1234, 1, frames)
+    threads = _pick_threads(wo, p, mels)
     try:
         from threadpoolctl import threadpool_limits
         ctx = threadpool_limits(limits=threads)
     except Exception:
         ctx = contextlib.nullcontext()
     with ctx:
-        p = wo.as_params(synth.synth_state_dict(0))
-        mels = synth.synth_mels(1234, 1, frames)
         probe = wo.generate(p, mels, max_steps=300, seed=0)      # includes the one-shot conditioning network
         per_step = max(probe['seconds'] / 300, 1e-6)
         steps = int(min(frames * HOP, max(300, max_seconds / per_step)))

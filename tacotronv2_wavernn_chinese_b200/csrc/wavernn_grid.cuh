@@ -26,7 +26,11 @@
 namespace b200tts {
 
 #ifndef B200_GRID_NW_WIDE
-#define B200_GRID_NW_WIDE 8            // wide mapping: warps per CTA (measured: 12 warps spill at 168 regs and lose)
+#define B200_GRID_NW_WIDE 16           // wide mapping: warps per CTA.  Measured at B=256: 8 warps (255 regs, 4x12 tiles) 80.5 us,
+                                       // 12 warps (168 regs) spill, 16 warps (128 regs, 4x6 tiles via row slices) 73.5 us
+#endif
+#ifndef B200_GRID_PD16
+#define B200_GRID_PD16 1              // columns of look-ahead in the 16-warp build (register budget 128)
 #endif
 #ifndef B200_GRID_PF
 #define B200_GRID_PF 0                 // explicit activation prefetch distance (0 = leave it to ptxas: measured fastest)
@@ -219,7 +223,8 @@ __device__ __forceinline__ void wide_accumulate_pd(float (&acc)[RT][U], const fl
 template <int U, int RT>
 __device__ __forceinline__ void wide_accumulate(float (&acc)[RT][U], const float* __restrict__ W, int ldw, int col4,
                                                 const float* __restrict__ act, int Bp, int u0, int lo, int hi) {
-  constexpr int PD = 2;   // measured on B200: 3-4 columns ahead on the 4/8-row tiles is SLOWER (19.0k vs 15.5k cycles for fc1)
+  // measured on B200: 3-4 columns ahead on the 4/8-row tiles is SLOWER (19.0k vs 15.5k cycles for fc1)
+  constexpr int PD = (B200_GRID_NW_WIDE >= 16) ? B200_GRID_PD16 : 2;
   wide_accumulate_pd<U, RT, PD>(acc, W, ldw, col4, act, Bp, u0, lo, hi);
 }
 
@@ -227,29 +232,32 @@ __device__ __forceinline__ void wide_accumulate(float (&acc)[RT][U], const float
 // Partial sums land in part[((g*KS + ks)*RT + r)*BT + ul].
 // (Measured: sharing one __noinline__ copy of this body between phases to shrink the ~65 KB kernel is SLOWER, 104.9 vs
 // 97.8 us per lock-step at B=256 -- the call/stack traffic costs more than the instruction-fetch stalls it removes.)
-template <int NW, int U, int UW, int RT, int NG>
+template <int NW, int U, int UW, int RT, int NG, int RS = 1>
 __device__ __forceinline__ void wide_partials(float* part, const Gemm& g0, const Gemm& g1, int tile_base, int Bp, int warp,
                                               int lane) {
-  constexpr int KS = NW / (NG * UW);
+  // warps = NG GEMMs x UW utterance warps x RS row slices x KS k slices; a thread owns U utterances x RT/RS rows
+  constexpr int KS = NW / (NG * UW * RS);
   constexpr int BT = 32 * U * UW;
-  static_assert(KS >= 1 && KS * NG * UW == NW, "warps must factor as NG x UW x KS");
-  const int g = warp / (UW * KS), rem = warp % (UW * KS), uw = rem / KS, ks = rem % KS;
+  constexpr int RTT = RT / RS;
+  static_assert(KS >= 1 && KS * NG * UW * RS == NW && RTT * RS == RT, "warps must factor as NG x UW x RS x KS");
+  const int g = warp / (UW * RS * KS), rem = warp % (UW * RS * KS), uw = rem / (RS * KS), rs = (rem / KS) % RS, ks = rem % KS;
   const Gemm& G = (NG == 2 && g == 1) ? g1 : g0;
   const int ul = uw * 32 * U + lane * U;
-  float acc[RT][U];
+  float acc[RTT][U];
 #pragma unroll
-  for (int r = 0; r < RT; ++r)
+  for (int r = 0; r < RTT; ++r)
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[r][u] = 0.f;
   int N4 = G.seg[0].n4 + (G.nseg > 1 ? G.seg[1].n4 : 0);
   const int lo = N4 * ks / KS, hi = N4 * (ks + 1) / KS;
+  const float* Wr = G.W + (size_t)rs * RTT * G.ldw;
   int col = 0;
   if constexpr (NG == 2) {                        // the big 2-GEMM phase: segments unrolled (measured faster for P2)
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       if (s < G.nseg) {
         const int a = max(lo, col), b = min(hi, col + G.seg[s].n4);
-        if (a < b) wide_accumulate<U, RT>(acc, G.W, G.ldw, col, G.seg[s].act, Bp, tile_base + ul, a - col, b - col);
+        if (a < b) wide_accumulate<U, RTT>(acc, Wr, G.ldw, col, G.seg[s].act, Bp, tile_base + ul, a - col, b - col);
         col += G.seg[s].n4;
       }
     }
@@ -257,37 +265,13 @@ __device__ __forceinline__ void wide_partials(float* part, const Gemm& g0, const
 #pragma unroll 1
     for (int s = 0; s < G.nseg; ++s) {            // runtime loop: one copy of the GEMM body per call site
       const int a = max(lo, col), b = min(hi, col + G.seg[s].n4);
-      if (a < b) wide_accumulate<U, RT>(acc, G.W, G.ldw, col, G.seg[s].act, Bp, tile_base + ul, a - col, b - col);
+      if (a < b) wide_accumulate<U, RTT>(acc, Wr, G.ldw, col, G.seg[s].act, Bp, tile_base + ul, a - col, b - col);
       col += G.seg[s].n4;
     }
   }
-  float* dst = part + (size_t)((g * KS + ks) * RT) * BT + ul;
+  float* dst = part + (size_t)((g * KS + ks) * RT + rs * RTT) * BT + ul;
 #pragma unroll
-  for (int r = 0; r < RT; ++r) ActLoad<U>::st(dst + r * BT, acc[r]);
-}
-
-// P01 cond rows (K = feat + aux = 112 is tiny): no k split -- warps = UW utterance warps x RG row groups, each row group
-// takes 16/RG of the 16 rows over all columns; results go straight to resA[row*BT + ul].
-template <int NWG, int U, int UW>
-__device__ __forceinline__ void wide_cond_rows(float* resA, const float* __restrict__ Wsm, int ldC, const Seg& s0, const Seg& s1,
-                                               int tile_base, int Bp, int warp, int lane) {
-  constexpr int RG = NWG / UW, RTA = 16 / RG, BT = 32 * U * UW;
-  static_assert(RG * RTA == 16, "row groups must tile the 16 cond rows");
-  const int uw = warp % UW, rg = warp / UW;
-  const int ul = uw * 32 * U + lane * U;
-  float acc[RTA][U];
-#pragma unroll
-  for (int r = 0; r < RTA; ++r)
-#pragma unroll
-    for (int u = 0; u < U; ++u) acc[r][u] = 0.f;
-  const float* W = Wsm + rg * RTA * ldC;
-#pragma unroll 1
-  for (int s = 0; s < 2; ++s) {
-    const Seg& sg = s ? s1 : s0;
-    wide_accumulate<U, RTA>(acc, W, ldC, s ? s0.n4 : 0, sg.act, Bp, tile_base + ul, 0, sg.n4);
-  }
-#pragma unroll
-  for (int r = 0; r < RTA; ++r) ActLoad<U>::st(resA + (size_t)(rg * RTA + r) * BT + ul, acc[r]);
+  for (int r = 0; r < RTT; ++r) ActLoad<U>::st(dst + r * BT, acc[r]);
 }
 
 // Narrow mapping (Bp == G <= 8): the whole activation vector of the phase is first staged into shared memory by all
@@ -354,20 +338,28 @@ template <int U, int UW, int GROUPS> struct MapTraits {
   static constexpr int NW = kGridWarpsWide;                                // warps per CTA
   static constexpr int NWG = NW / GROUPS;                                  // warps per group
   static constexpr int BT = 32 * U * UW;                                   // utterances per group tile
-  static constexpr int KS1 = NWG / UW;                                     // k slices of a 1-GEMM phase
-  static constexpr int KS2 = NWG / (2 * UW);                               // ... of a 2-GEMM phase
-  static constexpr int kPartFloats = (NWG / UW) * 3 * kUPC * BT;           // k-split partial sums of the largest GEMM phase
-  static constexpr int kGroupScratch = kPartFloats + 16 * BT;              // + the un-split cond rows of P01, per group
+  static constexpr int RS12 = (NW >= 16) ? 2 : 1;                          // row slices of the 12-row GRU tiles (16-warp build:
+                                                                           // 128 registers/thread -> 4 utterances x 6 rows)
+  static constexpr int KS1 = NWG / UW;                                     // k slices of the 4/8-row 1-GEMM phases (fc1/fc2/fc3)
+  static constexpr int KSB = NWG / (UW * RS12);                            // ... of the 12-row 1-GEMM pass of P01 (W_hh1)
+  static constexpr int KS2 = NWG / (2 * UW * RS12);                        // ... of the 2-GEMM phase (GRU 2)
+  static constexpr int kPartFloats = (KSB * 12 > KS1 * 8 ? KSB * 12 : KS1 * 8) * BT;   // largest partial-sum footprint
+  static constexpr int KSA = NWG / (UW * 4);                               // k slices of P01's 16 cond rows (4 row slices of 4)
+  static constexpr int kGroupScratch = kPartFloats + KSA * 16 * BT;        // + the cond-row partials of P01, per group
+  static_assert(KSA >= 1 && KSA * UW * 4 == NWG, "group warps must factor as UW x 4 x KSA");
   static constexpr int kScratchFloats = GROUPS * kGroupScratch;
-  static_assert(KS2 >= 1 && KS2 * 2 * UW == NWG, "group warps must factor as 2 x UW x KS2");
+  static_assert(KS2 >= 1 && KS2 * 2 * UW * RS12 == NWG, "group warps must factor as 2 x UW x RS12 x KS2");
 };
 template <int G> struct MapTraits<0, G, 1> {
   static constexpr bool kWide = false;
   static constexpr int NW = kGridWarpsNarrow;
   static constexpr int NWG = NW;
   static constexpr int BT = G;
+  static constexpr int RS12 = 1;
   static constexpr int KS1 = 1;
+  static constexpr int KSB = 1;
   static constexpr int KS2 = 1;
+  static constexpr int KSA = 1;
   static constexpr int kPartFloats = 0;
   static constexpr int kGroupScratch = 640 * G + 512 * G + 32 * G + 64;   // staged act A | act B | row results (16 + 12 rows)
   static constexpr int kScratchFloats = kGroupScratch;
@@ -392,7 +384,7 @@ template <int U, int UW, int GROUPS>
 __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_grid_kernel(GridModel M, GridArgs A) {
   using MT = MapTraits<U, UW, GROUPS>;
   constexpr int BT = MT::BT, NWG = MT::NWG, NT = NWG * 32;   // NT = threads of one group
-  constexpr int KS1 = MT::KS1, KS2 = MT::KS2;
+  constexpr int KS1 = MT::KS1, KS2 = MT::KS2, KSB = MT::KSB, KSA = MT::KSA, RS12 = MT::RS12;
   constexpr int G = MT::kWide ? 4 : UW;               // narrow: utterances per row; (unused value in wide mode)
   extern __shared__ __align__(16) float smem[];
   float* Wb = smem;                                   // this CTA's weights, resident for the whole kernel
@@ -463,10 +455,12 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
       const float* rB;        // gh partial sums (k slices) / rows
       if constexpr (MT::kWide) {
         float* resA = part + MT::kPartFloats;
-        wide_cond_rows<NWG, U, UW>(resA, Wb + M.oA_w, M.ldC, Seg{melT, M.FEAT / 4}, Seg{auxT, AUX / 4}, tb, Bp, warp, lane);
+        Gemm ga{};
+        ga.W = Wb + M.oA_w; ga.ldw = M.ldC; ga.nseg = 2; ga.seg[0] = Seg{melT, M.FEAT / 4}; ga.seg[1] = Seg{auxT, AUX / 4};
+        wide_partials<NWG, U, UW, 16, 1, 4>(resA, ga, ga, tb, Bp, warp, lane);
         Gemm gh{};
         gh.W = Wb + M.ohh1; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h1c, R / 4};
-        wide_partials<NWG, U, UW, 3 * kUPC, 1>(part, gh, gh, tb, Bp, warp, lane);
+        wide_partials<NWG, U, UW, 3 * kUPC, 1, RS12>(part, gh, gh, tb, Bp, warp, lane);
         rA = resA; rB = part;
       } else {
         stage_rows<NT>(stA, melT, M.FEAT * G, tid);
@@ -486,13 +480,13 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
         float hold;
         if constexpr (MT::kWide) hold = __ldcg(h1c + o);
         else hold = stB[(c * kUPC + j) * G + ul];
-        const float iout = fmaf(wAx[j], x, rA[(size_t)j * BT + ul]) + bA[j];
-        const float gir = fmaf(wAx[4 + j], x, rA[(size_t)(4 + j) * BT + ul]) + bA[4 + j];
-        const float giz = fmaf(wAx[4 + kUPC + j], x, rA[(size_t)(4 + kUPC + j) * BT + ul]) + bA[4 + kUPC + j];
-        const float gin = fmaf(wAx[4 + 2 * kUPC + j], x, rA[(size_t)(4 + 2 * kUPC + j) * BT + ul]) + bA[4 + 2 * kUPC + j];
-        float h = gru_update(gir, giz, gin, part_sum<KS1, 3 * kUPC, BT>(rB, 0, j, ul) + bhh[j],
-                             part_sum<KS1, 3 * kUPC, BT>(rB, 0, kUPC + j, ul) + bhh[kUPC + j],
-                             part_sum<KS1, 3 * kUPC, BT>(rB, 0, 2 * kUPC + j, ul) + bhh[2 * kUPC + j], hold);
+        const float iout = fmaf(wAx[j], x, part_sum<KSA, 16, BT>(rA, 0, j, ul)) + bA[j];
+        const float gir = fmaf(wAx[4 + j], x, part_sum<KSA, 16, BT>(rA, 0, 4 + j, ul)) + bA[4 + j];
+        const float giz = fmaf(wAx[4 + kUPC + j], x, part_sum<KSA, 16, BT>(rA, 0, 4 + kUPC + j, ul)) + bA[4 + kUPC + j];
+        const float gin = fmaf(wAx[4 + 2 * kUPC + j], x, part_sum<KSA, 16, BT>(rA, 0, 4 + 2 * kUPC + j, ul)) + bA[4 + 2 * kUPC + j];
+        float h = gru_update(gir, giz, gin, part_sum<KSB, 3 * kUPC, BT>(rB, 0, j, ul) + bhh[j],
+                             part_sum<KSB, 3 * kUPC, BT>(rB, 0, kUPC + j, ul) + bhh[kUPC + j],
+                             part_sum<KSB, 3 * kUPC, BT>(rB, 0, 2 * kUPC + j, ul) + bhh[2 * kUPC + j], hold);
         h1n[o] = h;
         A.x1[o] = iout + h;
       }
@@ -509,7 +503,7 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
         gi.W = Wb + M.oih2; gi.ldw = M.ldX; gi.nseg = 2; gi.seg[0] = Seg{A.x1, R / 4};
         gi.seg[1] = Seg{auxT + (size_t)AUX * Bp, AUX / 4};
         gh.W = Wb + M.ohh2; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h2c, R / 4};
-        wide_partials<NWG, U, UW, 3 * kUPC, 2>(part, gi, gh, tb, Bp, warp, lane);
+        wide_partials<NWG, U, UW, 3 * kUPC, 2, RS12>(part, gi, gh, tb, Bp, warp, lane);
       } else {
         stage_rows<NT>(stA, A.x1, R * G, tid);
         stage_rows<NT>(stA + R * G, auxT + (size_t)AUX * Bp, AUX * G, tid);
