@@ -300,7 +300,7 @@ def main():
             'gpu_launches': int(launches),
             'e2e': e2e,
         }
-        if not args.no_cpu_baseline and N >= 1:
+        if not args.no_cpu_baseline and N == 1:        # reported baseline: rank 0, single-GPU runs only
             rate, steps_run, threads = cpu_oracle_rate(T, max_seconds=15.0)
             line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
                                     'sample': f'1 utterance x {steps_run} of {S} steps, numpy oracle port of generate()'}

@@ -153,6 +153,7 @@ struct b200tts_wavernn {
   const float* d_fir = nullptr;   // [hop][NT]
   GridModel gm{};                 // per-CTA weight blobs of the grid kernel
   DeviceBuf grid_blob, mels_T, aux_T, grid_sync, grid_prof, fold_mels, fold_aux;
+  int* d_grid_error = nullptr;    // set by the grid kernel when a barrier wait timed out (a peer CTA vanished)
   int last_grid_ncta = 0;
   int coop = 0;
   // scratch
@@ -468,6 +469,13 @@ extern "C" double b200tts_wavernn_last_kernel_ms(b200tts_wavernn* ctx) {
     g_err = std::string("cudaEventElapsedTime: ") + cudaGetErrorString(e);
     return -1.0;
   }
+  if (ctx->d_grid_error) {
+    int flag = 0;
+    if (cudaMemcpy(&flag, ctx->d_grid_error, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess && flag) {
+      g_err = "grid kernel: a grid-barrier wait timed out (co-resident CTA missing); results are invalid";
+      return -1.0;
+    }
+  }
   return (double)ms;
 }
 
@@ -627,6 +635,7 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   a.best = ctx->grid_sync.as<unsigned long long>();
   a.barrier = reinterpret_cast<unsigned int*>(ctx->grid_sync.as<char>() + 2 * (size_t)Bp * sizeof(unsigned long long));
   a.error = reinterpret_cast<int*>(a.barrier + 96);
+  ctx->d_grid_error = a.error;
   a.mels_T = ctx->mels_T.as<float>();
   a.aux_T = ctx->aux_T.as<float>();
   a.B = B; a.Bp = Bp; a.S = S; a.T = T; a.hop = ua.hop; a.steps = ua.steps;
@@ -650,6 +659,14 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
     default: launch_grid_t<4, 2, 1>(ctx, a, st); break;
   }
   B200_CUDA(cudaEventRecord(ctx->ev1, st));
+}
+
+// After the stream has been synchronised: did the last grid launch abandon a barrier?
+static void check_grid_error(b200tts_wavernn* ctx) {
+  if (!ctx->d_grid_error) return;
+  int flag = 0;
+  B200_CUDA(cudaMemcpy(&flag, ctx->d_grid_error, sizeof(int), cudaMemcpyDeviceToHost));
+  REQUIRE(flag == 0, B200TTS_ECUDA, "grid kernel: a grid-barrier wait timed out (co-resident CTA missing); results are invalid");
 }
 
 static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
@@ -801,6 +818,7 @@ extern "C" int b200tts_wavernn_generate_host(b200tts_wavernn* ctx, const float* 
     std::memcpy(h_wave, ctx->h_stage.p, wav_bytes);
   }
   B200_CUDA(cudaStreamSynchronize(st));
+  check_grid_error(ctx);
   API_END
 }
 

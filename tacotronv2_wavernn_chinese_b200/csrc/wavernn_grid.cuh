@@ -2,7 +2,7 @@
 //
 // The 17.4 MB of fp32 step weights cannot live in one SM (228 KB), but they fit the chip: the grid is NCTA = R/4 = 128
 // co-resident CTAs (one per SM, cooperative launch), CTA c permanently holds in SHARED MEMORY the rows of every layer
-// that produce hidden units / fc rows [4c, 4c+4) and classes [8c, 8c+8) (136 KB), and all B utterances advance in
+// that produce hidden units / fc rows [4c, 4c+4) and classes [8c, 8c+8) (117 KB), and all B utterances advance in
 // lock step.  Per step each layer is a skinny GEMM  out[B, rows_c] = act[B, K] . W_c[rows_c, K]^T : the activations
 // ([K][Bp] fp32, K-major, L2-resident, 2 KB per utterance per layer) are the only thing that moves; weights never do.
 // Phases are separated by a grid-wide barrier (monotonic counter in L2, release/acquire).
@@ -18,8 +18,11 @@
 //   P5  fc3      (:223) + sampling (:232-235): every CTA owns 8 logits per utterance and joins a distributed
 //       argmax of (logit - log q), q ~ Exp(1), through one 64-bit atomicMax per (CTA, utterance)  [Gumbel-max ==
 //       Categorical(softmax(logits)).sample()]; the winner is read back by everybody at the next P0 (:235-237).
-// Two thread mappings: "wide" (lanes = utterances, register tile U utterances x RT rows, k split across warps) for
-// B >= 9, and "narrow" (lanes = k, warp-shuffle reductions) for B <= 8 where the step is pure latency.
+// Two thread mappings: "wide" for B >= 9 -- lanes = utterances, register tile 4 utterances x 6 rows, 16 warps factored as
+// (GEMM x utterance warp x row slice x k slice), k-slice partial sums through shared memory, two independent utterance
+// groups per CTA (own named barrier + grid-barrier counter each) so one group computes while the other sits in a
+// barrier -- and "narrow" for B <= 8 (activation vector staged into shared memory in one L2 round trip, lanes = k,
+// warp-shuffle reductions) where the step is pure latency.
 #pragma once
 #include "common.cuh"
 
@@ -31,9 +34,6 @@ namespace b200tts {
 #endif
 #ifndef B200_GRID_PD16
 #define B200_GRID_PD16 1              // columns of look-ahead in the 16-warp build (register budget 128)
-#endif
-#ifndef B200_GRID_PF
-#define B200_GRID_PF 0                 // explicit activation prefetch distance (0 = leave it to ptxas: measured fastest)
 #endif
 constexpr int kGridWarpsWide = B200_GRID_NW_WIDE;
 constexpr int kGridWarpsNarrow = 8;

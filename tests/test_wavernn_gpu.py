@@ -181,6 +181,18 @@ def test_batch_composition_invariance(torch_cuda, kernel):
             assert np.array_equal(solo['labels'].cpu().numpy()[0, :1500], full[b, :1500])
 
 
+@pytest.mark.parametrize('B', [33, 129, 300, 520])
+def test_grid_tiles_and_padding(torch_cuda, B):
+    """Batches that do not fill a tile / need several tiles per group: the grid kernel must give every row exactly what
+    it gives that row alone (Philox keyed by the global row), incl. the last row of a partially filled tile."""
+    eng, _ = engine_for('synth5')
+    mels = synth.synth_mels(900 + B, B, 21)
+    full = eng.generate(mels, seed=17, kernel='grid', max_steps=400)['labels'].cpu().numpy()
+    for b in (0, B // 2, B - 1):
+        solo = eng.generate(mels[b:b + 1], seed=17, utterance_offset=b, kernel='grid', max_steps=400)['labels'].cpu().numpy()
+        assert np.array_equal(solo[0, :400], full[b, :400]), f'row {b} of {B}'
+
+
 def test_kernels_agree_full_size(torch_cuda):
     """Both kernels, BASELINE-shaped batch (80-frame mels), free running with Philox: identical label streams for
     the first 3000 steps (beyond that fp32 re-association differences may flip a sampling near-tie)."""
