@@ -93,4 +93,29 @@ __device__ __forceinline__ float label_to_float(int label, float ncls_m1) {
   return 2.0f * (float)label / ncls_m1 - 1.0f;
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA bulk copy global -> shared (cp.async.bulk, completion through an mbarrier transaction count)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n B200_WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra B200_DONE_%=;\n"
+      " bra B200_WAIT_%=;\n B200_DONE_%=:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
 }  // namespace b200tts

@@ -32,6 +32,9 @@ namespace b200tts {
 #define B200_GRID_NW_WIDE 16           // wide mapping: warps per CTA.  Measured at B=256: 8 warps (255 regs, 4x12 tiles) 80.5 us,
                                        // 12 warps (168 regs) spill, 16 warps (128 regs, 4x6 tiles via row slices) 73.5 us
 #endif
+#ifndef B200_GRID_PD16_SMALL
+#define B200_GRID_PD16_SMALL 1        // ... for the 4/8-row tiles (fc phases), which have registers to spare
+#endif
 #ifndef B200_GRID_PD16
 #define B200_GRID_PD16 1              // columns of look-ahead in the 16-warp build (register budget 128)
 #endif
@@ -224,7 +227,7 @@ template <int U, int RT>
 __device__ __forceinline__ void wide_accumulate(float (&acc)[RT][U], const float* __restrict__ W, int ldw, int col4,
                                                 const float* __restrict__ act, int Bp, int u0, int lo, int hi) {
   // measured on B200: 3-4 columns ahead on the 4/8-row tiles is SLOWER (19.0k vs 15.5k cycles for fc1)
-  constexpr int PD = (B200_GRID_NW_WIDE >= 16) ? B200_GRID_PD16 : 2;
+  constexpr int PD = (B200_GRID_NW_WIDE >= 16) ? ((RT * U <= 32) ? B200_GRID_PD16_SMALL : B200_GRID_PD16) : 2;
   wide_accumulate_pd<U, RT, PD>(acc, W, ldw, col4, act, Bp, u0, lo, hi);
 }
 
@@ -402,9 +405,18 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
   const int R = M.R, F = M.F, AUX = M.AUX;
   const float ncls_m1 = (float)(M.NC - 1);
   {
-    const float4* src = reinterpret_cast<const float4*>(A.wblob + (size_t)c * M.blob);
-    float4* dst = reinterpret_cast<float4*>(Wb);
-    for (int i = threadIdx.x; i < M.blob / 4; i += GROUPS * NT) dst[i] = __ldg(src + i);
+    // one-time load of this CTA's 117 KB weight blob: TMA bulk copies (UBLKCP) signalled through an mbarrier
+    __shared__ __align__(8) unsigned long long wbar;
+    const char* src = reinterpret_cast<const char*>(A.wblob + (size_t)c * M.blob);
+    const unsigned total = (unsigned)M.blob * 4u;
+    if (threadIdx.x == 0) mbar_init(&wbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&wbar, total);
+      for (unsigned off = 0; off < total; off += 32768u)
+        tma_bulk_g2s(reinterpret_cast<char*>(Wb) + off, src + off, min(32768u, total - off), &wbar);
+    }
+    mbar_wait(&wbar, 0);
   }
   __syncthreads();
   unsigned int nbar = 0;

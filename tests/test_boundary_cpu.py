@@ -169,3 +169,20 @@ print("OK")
 '''
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
     assert r.returncode == 0 and 'OK' in r.stdout, r.stdout + r.stderr
+
+
+def test_fold_geometry_matches_reference_formula():
+    """b200tts_wavernn_fold_geometry needs no GPU: (n_folds, fold_len) of fold_with_overlap (fatchord_version.py:319-330)."""
+    lib, L = _lib()
+    for T, target, overlap in [(80, 11000, 550), (30, 2750, 550), (30, 2700, 500), (402, 11000, 550), (21, 100, 20)]:
+        S = T * 275
+        nf = (S - overlap) // (target + overlap)
+        if S - (nf * (target + overlap) + overlap) != 0:
+            nf += 1
+        a, b = ctypes.c_int(), ctypes.c_int()
+        assert lib.b200tts_wavernn_fold_geometry(T, 275, target, overlap, ctypes.byref(a), ctypes.byref(b)) == 0
+        assert (a.value, b.value) == (nf, target + 2 * overlap)
+        x = np.zeros((1, S, 1), dtype=np.float32)
+        assert wo.fold_with_overlap(x, target, overlap).shape[:2] == (nf, target + 2 * overlap)
+    assert lib.b200tts_wavernn_fold_geometry(2, 275, 100, 600, ctypes.byref(a), ctypes.byref(b)) != 0     # shorter than the overlap
+    assert b'overlap' in lib.b200tts_last_error()
