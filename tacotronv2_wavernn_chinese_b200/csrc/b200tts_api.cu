@@ -559,15 +559,16 @@ static void launch_grid_t(b200tts_wavernn* ctx, GridArgs& a, cudaStream_t st) {
 }
 
 // Mapping for B utterances: returns the padded batch; variant = index into the dispatch table below.
-enum { GV_N4, GV_N8, GV_W1, GV_W1x2, GV_W2x2, GV_W4x2, GV_W4_2 };
+enum { GV_N4, GV_N8, GV_W1, GV_W1x2, GV_W2x2, GV_W4x2, GV_W4_2, GV_W2, GV_W4 };
 static int grid_variant(int B, int* variant) {
   static const bool single = getenv("B200TTS_GRID_SINGLE_GROUP") != nullptr;   // A/B switch for measurements
   if (B <= 4) { *variant = GV_N4; return 4; }
   if (B <= 8) { *variant = GV_N8; return 8; }
   if (B <= 32) { *variant = GV_W1; return 32; }
   if (single) { *variant = GV_W4_2; return (B + 255) / 256 * 256; }
-  if (B <= 64) { *variant = GV_W1x2; return 64; }
-  if (B <= 128) { *variant = GV_W2x2; return 128; }
+  static const bool mid_dual = getenv("B200TTS_GRID_MID_DUAL") != nullptr;       // A/B switch: old mid-batch mapping
+  if (B <= 64) { *variant = mid_dual ? GV_W1x2 : GV_W2; return 64; }
+  if (B <= 128) { *variant = mid_dual ? GV_W2x2 : GV_W4; return 128; }
   *variant = GV_W4x2;
   return (B + 255) / 256 * 256;
 }
@@ -656,6 +657,8 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
     case GV_W1x2: launch_grid_t<1, 1, 2>(ctx, a, st); break;
     case GV_W2x2: launch_grid_t<2, 1, 2>(ctx, a, st); break;
     case GV_W4x2: launch_grid_t<4, 1, 2>(ctx, a, st); break;
+    case GV_W2: launch_grid_t<2, 1, 1>(ctx, a, st); break;
+    case GV_W4: launch_grid_t<4, 1, 1>(ctx, a, st); break;
     default: launch_grid_t<4, 2, 1>(ctx, a, st); break;
   }
   B200_CUDA(cudaEventRecord(ctx->ev1, st));
