@@ -26,6 +26,7 @@ def main(argv=None):
     ap.add_argument('--text', required=True, help='pinyin tokens separated by spaces (or Hanzi if the pinyin front-end is importable)')
     ap.add_argument('--checkpoint', default='logs-Tacotron-2/taco_pretrained', help='TF checkpoint prefix or directory')
     ap.add_argument('--train_txt', default=hparams.tacotron_input, help='training list the symbol table is rebuilt from')
+    ap.add_argument('--symbols_json', default=None, help='JSON file with a "symbols" list (instead of scanning --train_txt)')
     ap.add_argument('--hparams', default='', help='comma separated name=value overrides')
     ap.add_argument('--out_dir', default='tacotron_inference_output')
     ap.add_argument('--seed', type=int, default=0, help='Philox seed of the (always on) prenet dropout')
@@ -38,7 +39,11 @@ def main(argv=None):
             _, text = get_pyin(text)
         except Exception as e:
             raise SystemExit(f'Hanzi input needs the reference pinyin front-end on PYTHONPATH ({e}); pass pinyin tokens instead')
-    synth = Synthesizer().load(args.checkpoint, hp, train_txt=args.train_txt)
+    symbols = None
+    if args.symbols_json:
+        import json
+        symbols = json.load(open(args.symbols_json, encoding='utf-8'))['symbols']
+    synth = Synthesizer().load(args.checkpoint, hp, symbols=symbols, train_txt=args.train_txt)
     idx = hashlib.md5(text.encode('utf8')).hexdigest()
     t0 = time.time()
     mel_path, align_path = synth.synthesize(text, args.out_dir, idx, seed=args.seed)

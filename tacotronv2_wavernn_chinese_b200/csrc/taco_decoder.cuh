@@ -139,7 +139,11 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 __global__ void __launch_bounds__(kTacoThreads, 1) taco_decoder_kernel(TacoWeights W, TacoArgs A) {
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int Tx = A.lengths[b];
+  const int Tx = min(A.lengths[b], A.Tx_max);
+  if (Tx < 1) {                                        // empty sentence: nothing to attend to
+    if (tid == 0) A.nsteps[b] = 0;
+    return;
+  }
   const int P = W.P, U = W.U, E = W.E, AD = W.A, NF = W.NF, KW = W.KW, M = W.mels;
   // ---- shared memory carve-up ----
   float* x = sm;                       // [M]          previous frame

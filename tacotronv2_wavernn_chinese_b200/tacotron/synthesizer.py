@@ -30,7 +30,10 @@ class Synthesizer:
 
     def load(self, checkpoint_path, hparams=None, symbols=None, train_txt='train.txt', device=None):
         """checkpoint_path: TF checkpoint prefix or the directory holding the `checkpoint` pointer file (:138-139)."""
-        w = ckpt.load_tacotron_weights(checkpoint_path)
+        if str(checkpoint_path).endswith('.npz'):          # variables already extracted from the TF bundle (np.savez of ckpt.load_tacotron_weights)
+            w = dict(np.load(checkpoint_path))
+        else:
+            w = ckpt.load_tacotron_weights(checkpoint_path)
         self.step = int(w.get('global_step', 0))
         if symbols is None:
             symbols = build_symbols(train_txt)

@@ -27,7 +27,8 @@ def test_symbol_table_pin():
     s = sentences()
     assert len(s['symbols']) == 191 and s['symbols'][:2] == ['_', '~']
     assert s['symbols'][2:] == sorted(s['symbols'][2:])
-    assert all(len(v['ids']) == 51 and v['ids'][-1] == 1 for v in s['sentences'].values())
+    assert all(len(s['sentences'][k]['ids']) == 51 for k in ('241', '378', '407'))      # the 50-token sentences of config 4
+    assert len(s['sentences']) == 67 and all(v['ids'][-1] == 1 and min(v['ids']) >= 1 for v in s['sentences'].values())
 
 
 def test_oracle_aligns_and_stops_on_a_training_sentence():
