@@ -1,29 +1,48 @@
-"""Checkpoint / output locations, same attribute names as the reference's `wavernn/utils/paths.py:6-34`."""
+"""Checkpoint / output locations of the vocoder.
+
+Exposes the attribute names the reference's `wavernn/utils/paths.py` object has (`voc_checkpoints`,
+`voc_latest_weights`, `voc_latest_optim`, `voc_output`, `voc_step`, `voc_log`, `get_voc_named_*`), because
+`wavernn_gen.py` and user scripts read them.  Unlike the reference (anchored three directories above its own source
+file) the tree is anchored at `base`, default: $B200TTS_BASE or the working directory, so the shipped
+`logs_wavernn/checkpoints/latest_weights.pyt` is found next to wherever `wavernn_gen.py` is run.
+"""
 from __future__ import annotations
 
 import os
 from pathlib import Path
 
+_LAYOUT = {                                   # attribute -> path below `base`
+    'voc_checkpoints': 'logs_wavernn/checkpoints',
+    'voc_output': 'logs_wavernn/model_outputs',
+}
+_CHECKPOINT_FILES = {                         # attribute -> file inside voc_checkpoints
+    'voc_latest_weights': 'latest_weights.pyt',
+    'voc_latest_optim': 'latest_optim.pyt',
+    'voc_step': 'step.npy',
+    'voc_log': 'log.txt',
+}
+
 
 class Paths:
     def __init__(self, voc_id, base=None):
-        # the reference anchors at the repository root (three levels above its utils/paths.py); here the root is
-        # the working directory unless given, so the shipped `logs_wavernn/` tree is found next to wavernn_gen.py
-        self.base = Path(base if base is not None else os.environ.get('B200TTS_BASE', os.getcwd())).expanduser().resolve()
-        self.voc_checkpoints = self.base / 'logs_wavernn/checkpoints'
-        self.voc_latest_weights = self.voc_checkpoints / 'latest_weights.pyt'
-        self.voc_latest_optim = self.voc_checkpoints / 'latest_optim.pyt'
-        self.voc_output = self.base / 'logs_wavernn/model_outputs'
-        self.voc_step = self.voc_checkpoints / 'step.npy'
-        self.voc_log = self.voc_checkpoints / 'log.txt'
+        self.voc_id = voc_id
+        root = base if base is not None else os.environ.get('B200TTS_BASE', os.getcwd())
+        self.base = Path(root).expanduser().resolve()
+        for attr, rel in _LAYOUT.items():
+            setattr(self, attr, self.base / rel)
+        for attr, name in _CHECKPOINT_FILES.items():
+            setattr(self, attr, self.voc_checkpoints / name)
         self.create_paths()
 
     def create_paths(self):
-        os.makedirs(self.voc_checkpoints, exist_ok=True)
-        os.makedirs(self.voc_output, exist_ok=True)
+        for attr in _LAYOUT:
+            getattr(self, attr).mkdir(parents=True, exist_ok=True)
+
+    def _named(self, name, kind):
+        return self.voc_checkpoints / f'{name}_{kind}.pyt'
 
     def get_voc_named_weights(self, name):
-        return self.voc_checkpoints / f'{name}_weights.pyt'
+        return self._named(name, 'weights')
 
     def get_voc_named_optim(self, name):
-        return self.voc_checkpoints / f'{name}_optim.pyt'
+        return self._named(name, 'optim')
