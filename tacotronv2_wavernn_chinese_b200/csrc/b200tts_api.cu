@@ -367,7 +367,12 @@ extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b
     g.obhh1 = take(3 * kUPC); g.obih2 = take(3 * kUPC); g.obhh2 = take(3 * kUPC);
     g.obfc1 = take(kUPC); g.obfc2 = take(kUPC); g.obfc3 = take(kCPC);
     g.blob = off;
-    size_t smem_need = ((size_t)g.blob + (size_t)MapTraits<4, 2, 1>::kScratchFloats) * sizeof(float) + 2048;
+    constexpr int kMaxScratch = std::max({MapTraits<0, 4, 1>::kScratchFloats, MapTraits<0, 8, 1>::kScratchFloats,
+                                          MapTraits<1, 1, 1>::kScratchFloats, MapTraits<2, 1, 1>::kScratchFloats,
+                                          MapTraits<4, 1, 1>::kScratchFloats, MapTraits<1, 1, 2>::kScratchFloats,
+                                          MapTraits<2, 1, 2>::kScratchFloats, MapTraits<4, 1, 2>::kScratchFloats,
+                                          MapTraits<2, 2, 2>::kScratchFloats});   // every variant launch_grid can dispatch
+    size_t smem_need = ((size_t)g.blob + (size_t)kMaxScratch) * sizeof(float) + 2048;
     if (smem_need > 227 * 1024) g.ok = 0;
     B200_CUDA(cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, device));
     if (!ctx->coop) g.ok = 0;
@@ -559,17 +564,16 @@ static void launch_grid_t(b200tts_wavernn* ctx, GridArgs& a, cudaStream_t st) {
 }
 
 // Mapping for B utterances: returns the padded batch; variant = index into the dispatch table below.
-enum { GV_N4, GV_N8, GV_W1, GV_W1x2, GV_W2x2, GV_W4x2, GV_W4_2, GV_W2, GV_W4 };
+enum { GV_N4, GV_N8, GV_W1, GV_W1x2, GV_W2x2, GV_W4x2, GV_W2, GV_W4, GV_W2_2x2 };
 static int grid_variant(int B, int* variant) {
-  static const bool single = getenv("B200TTS_GRID_SINGLE_GROUP") != nullptr;   // A/B switch for measurements
   if (B <= 4) { *variant = GV_N4; return 4; }
   if (B <= 8) { *variant = GV_N8; return 8; }
   if (B <= 32) { *variant = GV_W1; return 32; }
-  if (single) { *variant = GV_W4_2; return (B + 255) / 256 * 256; }
   static const bool mid_dual = getenv("B200TTS_GRID_MID_DUAL") != nullptr;       // A/B switch: old mid-batch mapping
   if (B <= 64) { *variant = mid_dual ? GV_W1x2 : GV_W2; return 64; }
   if (B <= 128) { *variant = mid_dual ? GV_W2x2 : GV_W4; return 128; }
-  *variant = GV_W4x2;
+  static const bool big22 = getenv("B200TTS_GRID_BIG_2X2") != nullptr;         // A/B switch: 2 utt x 12 rows per thread, no row slices
+  *variant = big22 ? GV_W2_2x2 : GV_W4x2;
   return (B + 255) / 256 * 256;
 }
 
@@ -659,7 +663,8 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
     case GV_W4x2: launch_grid_t<4, 1, 2>(ctx, a, st); break;
     case GV_W2: launch_grid_t<2, 1, 1>(ctx, a, st); break;
     case GV_W4: launch_grid_t<4, 1, 1>(ctx, a, st); break;
-    default: launch_grid_t<4, 2, 1>(ctx, a, st); break;
+    case GV_W2_2x2: launch_grid_t<2, 2, 2>(ctx, a, st); break;
+    default: REQUIRE(false, B200TTS_EINVAL, "internal: unknown grid variant");
   }
   B200_CUDA(cudaEventRecord(ctx->ev1, st));
 }

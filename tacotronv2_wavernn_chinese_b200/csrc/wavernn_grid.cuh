@@ -120,20 +120,28 @@ __device__ __forceinline__ bool grid_barrier(unsigned int* ctr, unsigned int tar
 }
 
 // ---- activation loads (L2 only: these buffers are rewritten by other SMs every step) ----------------------------------
+#ifndef B200_GRID_ACT_L1
+#define B200_GRID_ACT_L1 0
+#endif
+#if B200_GRID_ACT_L1
+#define B200_ACT_LD __ldca     // through L1: legal because every grid barrier's ld.acquire.gpu invalidates L1 (CCTL.IVALL)
+#else
+#define B200_ACT_LD __ldcg
+#endif
 template <int U> struct ActLoad;
 template <> struct ActLoad<1> {
-  static __device__ __forceinline__ void ld(const float* p, float (&a)[1]) { a[0] = __ldcg(p); }
+  static __device__ __forceinline__ void ld(const float* p, float (&a)[1]) { a[0] = B200_ACT_LD(p); }
   static __device__ __forceinline__ void st(float* p, const float (&a)[1]) { p[0] = a[0]; }
 };
 template <> struct ActLoad<2> {
   static __device__ __forceinline__ void ld(const float* p, float (&a)[2]) {
-    float2 v = __ldcg(reinterpret_cast<const float2*>(p)); a[0] = v.x; a[1] = v.y;
+    float2 v = B200_ACT_LD(reinterpret_cast<const float2*>(p)); a[0] = v.x; a[1] = v.y;
   }
   static __device__ __forceinline__ void st(float* p, const float (&a)[2]) { *reinterpret_cast<float2*>(p) = make_float2(a[0], a[1]); }
 };
 template <> struct ActLoad<4> {
   static __device__ __forceinline__ void ld(const float* p, float (&a)[4]) {
-    float4 v = __ldcg(reinterpret_cast<const float4*>(p)); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    float4 v = B200_ACT_LD(reinterpret_cast<const float4*>(p)); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
   }
   static __device__ __forceinline__ void st(float* p, const float (&a)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
@@ -141,7 +149,7 @@ template <> struct ActLoad<4> {
 };
 template <> struct ActLoad<8> {
   static __device__ __forceinline__ void ld(const float* p, float (&a)[8]) {
-    float4 v = __ldcg(reinterpret_cast<const float4*>(p)), w = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+    float4 v = B200_ACT_LD(reinterpret_cast<const float4*>(p)), w = B200_ACT_LD(reinterpret_cast<const float4*>(p) + 1);
     a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; a[4] = w.x; a[5] = w.y; a[6] = w.z; a[7] = w.w;
   }
 };
@@ -161,18 +169,39 @@ struct Gemm {           // rows x (sum of segs) weight block in shared memory
 // The activation loads come from L2 (~1 us under load) and only 3 warps share a scheduler, so they are software
 // pipelined two iterations (8 k rows) ahead in registers: three rotating buffers, loads of c4+2 issued before the
 // FMAs of c4.
+#ifndef B200_GRID_RS2_FULL
+#define B200_GRID_RS2_FULL 0
+#endif
+#ifndef B200_GRID_FFMA2
+#define B200_GRID_FFMA2 1
+#endif
 template <int U, int RT>
 __device__ __forceinline__ void wide_fma4(float (&acc)[RT][U], const float4* __restrict__ W4, int ldw4, int c4,
                                           const float (&a)[4][U]) {
 #pragma unroll
   for (int r = 0; r < RT; ++r) {
     float4 w = W4[r * ldw4 + c4];
+    if constexpr (B200_GRID_FFMA2 && U % 2 == 0) {
+      // sm_100 packed fp32: one FFMA2 does two utterances (a 64-bit register pair) against ONE weight register, which
+      // the instruction broadcasts (`FFMA2 Rd, Ra.F32x2.HI_LO, Rw.F32, Rd.F32x2.HI_LO`) -- half the issue slots of
+      // scalar FFMA for bit-identical results (same rounding, same summation order per lane).
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      acc[r][u] = fmaf(w.x, a[0][u], acc[r][u]);
-      acc[r][u] = fmaf(w.y, a[1][u], acc[r][u]);
-      acc[r][u] = fmaf(w.z, a[2][u], acc[r][u]);
-      acc[r][u] = fmaf(w.w, a[3][u], acc[r][u]);
+      for (int u = 0; u < U; u += 2) {
+        float2 s = make_float2(acc[r][u], acc[r][u + 1]);
+        s = __ffma2_rn(make_float2(a[0][u], a[0][u + 1]), make_float2(w.x, w.x), s);
+        s = __ffma2_rn(make_float2(a[1][u], a[1][u + 1]), make_float2(w.y, w.y), s);
+        s = __ffma2_rn(make_float2(a[2][u], a[2][u + 1]), make_float2(w.z, w.z), s);
+        s = __ffma2_rn(make_float2(a[3][u], a[3][u + 1]), make_float2(w.w, w.w), s);
+        acc[r][u] = s.x; acc[r][u + 1] = s.y;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[r][u] = fmaf(w.x, a[0][u], acc[r][u]);
+        acc[r][u] = fmaf(w.y, a[1][u], acc[r][u]);
+        acc[r][u] = fmaf(w.z, a[2][u], acc[r][u]);
+        acc[r][u] = fmaf(w.w, a[3][u], acc[r][u]);
+      }
     }
   }
 }
@@ -341,17 +370,20 @@ template <int U, int UW, int GROUPS> struct MapTraits {
   static constexpr int NW = kGridWarpsWide;                                // warps per CTA
   static constexpr int NWG = NW / GROUPS;                                  // warps per group
   static constexpr int BT = 32 * U * UW;                                   // utterances per group tile
-  static constexpr int RS12 = (NW >= 16) ? 2 : 1;                          // row slices of the 12-row GRU tiles (16-warp build:
+  static constexpr int RS12 = (NW >= 16 && UW == 1) ? 2 : 1;               // row slices of the 12-row GRU tiles (16-warp build:
                                                                            // 128 registers/thread -> 4 utterances x 6 rows)
   static constexpr int KS1 = NWG / UW;                                     // k slices of the 4/8-row 1-GEMM phases (fc1/fc2/fc3)
   static constexpr int KSB = NWG / (UW * RS12);                            // ... of the 12-row 1-GEMM pass of P01 (W_hh1)
-  static constexpr int KS2 = NWG / (2 * UW * RS12);                        // ... of the 2-GEMM phase (GRU 2)
-  static constexpr int kPartFloats = (KSB * 12 > KS1 * 8 ? KSB * 12 : KS1 * 8) * BT;   // largest partial-sum footprint
+  static constexpr int RS2 = (B200_GRID_RS2_FULL && U == 4 && GROUPS == 2) ? 1 : RS12;   // row slices in the 2-GEMM phase (GRU 2)
+  static constexpr int KS2 = NWG / (2 * UW * RS2);                         // ... of the 2-GEMM phase (GRU 2)
+  static constexpr int kPartRows = KSB * 12 > KS1 * 8 ? KSB * 12 : KS1 * 8;
+  static constexpr int kPartFloats = (kPartRows > 2 * KS2 * 12 ? kPartRows : 2 * KS2 * 12) * BT;   // largest partial-sum footprint
   static constexpr int KSA = NWG / (UW * 4);                               // k slices of P01's 16 cond rows (4 row slices of 4)
-  static constexpr int kGroupScratch = kPartFloats + KSA * 16 * BT;        // + the cond-row partials of P01, per group
+  static constexpr int kCondOff = KSB * 12 * BT;                           // P01: cond-row partials sit behind the W_hh1 partials
+  static constexpr int kGroupScratch = kPartFloats > kCondOff + KSA * 16 * BT ? kPartFloats : kCondOff + KSA * 16 * BT;
   static_assert(KSA >= 1 && KSA * UW * 4 == NWG, "group warps must factor as UW x 4 x KSA");
   static constexpr int kScratchFloats = GROUPS * kGroupScratch;
-  static_assert(KS2 >= 1 && KS2 * 2 * UW * RS12 == NWG, "group warps must factor as 2 x UW x RS12 x KS2");
+  static_assert(KS2 >= 1 && KS2 * 2 * UW * RS2 == NWG, "group warps must factor as 2 x UW x RS2 x KS2");
 };
 template <int G> struct MapTraits<0, G, 1> {
   static constexpr bool kWide = false;
@@ -359,6 +391,7 @@ template <int G> struct MapTraits<0, G, 1> {
   static constexpr int NWG = NW;
   static constexpr int BT = G;
   static constexpr int RS12 = 1;
+  static constexpr int RS2 = 1;
   static constexpr int KS1 = 1;
   static constexpr int KSB = 1;
   static constexpr int KS2 = 1;
@@ -466,7 +499,7 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
       const float* rA;        // [16][BT]: cond part of the 4 I rows and the 12 folded gi rows
       const float* rB;        // gh partial sums (k slices) / rows
       if constexpr (MT::kWide) {
-        float* resA = part + MT::kPartFloats;
+        float* resA = part + MT::kCondOff;
         Gemm ga{};
         ga.W = Wb + M.oA_w; ga.ldw = M.ldC; ga.nseg = 2; ga.seg[0] = Seg{melT, M.FEAT / 4}; ga.seg[1] = Seg{auxT, AUX / 4};
         wide_partials<NWG, U, UW, 16, 1, 4>(resA, ga, ga, tb, Bp, warp, lane);
@@ -515,7 +548,7 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
         gi.W = Wb + M.oih2; gi.ldw = M.ldX; gi.nseg = 2; gi.seg[0] = Seg{A.x1, R / 4};
         gi.seg[1] = Seg{auxT + (size_t)AUX * Bp, AUX / 4};
         gh.W = Wb + M.ohh2; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h2c, R / 4};
-        wide_partials<NWG, U, UW, 3 * kUPC, 2, RS12>(part, gi, gh, tb, Bp, warp, lane);
+        wide_partials<NWG, U, UW, 3 * kUPC, 2, MT::RS2>(part, gi, gh, tb, Bp, warp, lane);
       } else {
         stage_rows<NT>(stA, A.x1, R * G, tid);
         stage_rows<NT>(stA + R * G, auxT + (size_t)AUX * Bp, AUX * G, tid);
