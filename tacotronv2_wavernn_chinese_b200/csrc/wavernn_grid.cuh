@@ -97,26 +97,45 @@ __device__ __forceinline__ void group_sync(int grp) {
   else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NTG) : "memory");
 }
 
-// All threads of the group call.  `target` = (number of barriers passed so far + 1) * gridDim.x.  False on timeout.
+// The grid barrier in two halves so that work which does not depend on the other CTAs can sit between them.
+// `grid_arrive`: all threads of the group call, after their last global write of the phase.
+// `grid_wait`:   all threads of the group call; `target` = (number of barriers arrived at so far) * gridDim.x.  False on
+//                timeout (a co-resident CTA is gone): the caller returns instead of hanging the GPU.
+#ifndef B200_GRID_SPLIT_BARRIER
+#define B200_GRID_SPLIT_BARRIER 2   // single-group kernels only.  0: plain barriers; 1: P01's GEMMs run before the wait on
+#endif                              // P5's barrier; 2: also GRU-2's W_hh pass starts before the wait on P01's barrier
 template <int GROUPS, int NTG>
-__device__ __forceinline__ bool grid_barrier(unsigned int* ctr, unsigned int target, int* error, int grp, int gtid) {
-  __shared__ int s_ok[2];
+__device__ __forceinline__ void grid_arrive(unsigned int* ctr, int grp, int gtid) {
   group_sync<GROUPS, NTG>(grp);
-  if (gtid == 0) {
-    red_release_add_u32(ctr, 1u);                 // release: orders this group's prior global writes (cumulative via bar.sync)
-    int ok = 1;
-    long long t0 = clock64();
-    while (ld_acquire_u32(ctr) < target) {
-      if (clock64() - t0 > 4000000000LL) {        // ~2 s: a peer CTA is gone; bail out instead of hanging the GPU
-        ok = 0;
-        atomicExch(error, 1);
-        break;
-      }
+  if (gtid == 0) red_release_add_u32(ctr, 1u);    // release: orders this group's prior global writes (cumulative via bar.sync)
+}
+__device__ __forceinline__ int grid_spin(const unsigned int* ctr, unsigned int target, int* error) {
+  long long t0 = clock64();
+  while (ld_acquire_u32(ctr) < target) {
+    if (clock64() - t0 > 4000000000LL) {          // ~2 s: a peer CTA is gone; bail out instead of hanging the GPU
+      atomicExch(error, 1);
+      return 0;
     }
-    s_ok[grp] = ok;
   }
+  return 1;
+}
+template <int GROUPS, int NTG>
+__device__ __forceinline__ bool grid_wait(unsigned int* ctr, unsigned int target, int* error, int grp, int gtid, int* s_ok) {
+  if (gtid == 0) s_ok[grp] = grid_spin(ctr, target, error);
   group_sync<GROUPS, NTG>(grp);
   return s_ok[grp] != 0;
+}
+template <int GROUPS, int NTG>
+__device__ __forceinline__ bool grid_barrier(unsigned int* ctr, unsigned int target, int* error, int grp, int gtid, int* s_ok) {
+  grid_arrive<GROUPS, NTG>(ctr, grp, gtid);
+  return grid_wait<GROUPS, NTG>(ctr, target, error, grp, gtid, s_ok);
+}
+// Only the first `NSUB` threads of the group wait (named barrier 3 + grp); the rest of the group carries on and meets
+// them at the next group_sync.  The outcome is left in s_ok[grp] for everybody to read after that group_sync.
+template <int NSUB>
+__device__ __forceinline__ void grid_wait_sub(unsigned int* ctr, unsigned int target, int* error, int grp, int gtid, int* s_ok) {
+  if (gtid == 0) s_ok[grp] = grid_spin(ctr, target, error);
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 3), "r"(NSUB) : "memory");
 }
 
 // ---- activation loads (L2 only: these buffers are rewritten by other SMs every step) ----------------------------------
@@ -454,6 +473,13 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
   __syncthreads();
   unsigned int nbar = 0;
   const unsigned int ncta = gridDim.x;
+  __shared__ int s_ok[2];                             // outcome of the group's last barrier wait
+  // Split barriers pay off when ONE group owns the SM (B <= 128: 18.7 -> 17.7 us per step at B = 1, 30.4 -> 29.4 at 32,
+  // 42.4 -> 41.9 at 128).  With two groups the other group already fills the barrier bubble and the split is slower
+  // (68.2 -> 74.5 us at B = 256 measured), so it is off there.
+  constexpr int kSplit = (GROUPS == 1) ? B200_GRID_SPLIT_BARRIER : 0;
+  bool pending = false;                               // arrived at the sampling barrier of the previous step, not yet waited
+  unsigned int pend_target = 0;
   const size_t RB = (size_t)R * Bp;
   // narrow-mode scratch views
   float* stA = part;
@@ -483,18 +509,6 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
 
     // ================= P01: read back the previous step's winner; I layer folded into GRU 1 =================
     for (int tb = tb_lo; tb < tb_hi; tb += BT) {
-      for (int ul = tid; ul < BT; ul += NT) {
-        const int u = tb + ul;
-        float x = 0.f;
-        if (t > 0 && u < A.B) {
-          unsigned long long pk = __ldcg(A.best + (size_t)((t - 1) & 1) * Bp + u);
-          int label = (int)unpack_idx(pk);
-          if (c == 0) A.labels[(size_t)u * A.S + (t - 1)] = (int16_t)label;
-          int fb = A.teacher ? (int)A.teacher[(size_t)u * A.S + (t - 1)] : label;
-          x = label_to_float(fb, ncls_m1);
-        }
-        xs[ul] = x;
-      }
       const float* melT = A.mels_T + (size_t)t * M.FEAT * Bp;
       const float* rA;        // [16][BT]: cond part of the 4 I rows and the 12 folded gi rows
       const float* rB;        // gh partial sums (k slices) / rows
@@ -515,6 +529,26 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
         narrow_rows<G, 4>(nout, 0, Wb + M.oA_w, M.ldC, stA, M.ldC / 4, 16, 0, NWG / 2, warp, lane);
         narrow_rows<G, 3>(nout + 16 * G, 0, Wb + M.ohh1, R, stB, R / 4, 3 * kUPC, NWG / 2, NWG / 2, warp, lane);
         rA = nout; rB = nout + 16 * G;
+      }
+      // Everything above reads only the conditioning and h1(t-1).  The fed-back sample needs the sampling barrier of
+      // step t-1, which this group arrived at before starting the GEMMs: its latency and skew hide behind them.
+      if (pending) {
+        PROF_MARK(0);
+        if (!grid_wait<GROUPS, NT>(bar_ctr, pend_target, A.error, grp, tid, s_ok)) return;
+        pending = false;
+        PROF_MARK(11);
+      }
+      for (int ul = tid; ul < BT; ul += NT) {       // read back the previous step's winner
+        const int u = tb + ul;
+        float x = 0.f;
+        if (t > 0 && u < A.B) {
+          unsigned long long pk = __ldcg(A.best + (size_t)((t - 1) & 1) * Bp + u);
+          int label = (int)unpack_idx(pk);
+          if (c == 0) A.labels[(size_t)u * A.S + (t - 1)] = (int16_t)label;
+          int fb = A.teacher ? (int)A.teacher[(size_t)u * A.S + (t - 1)] : label;
+          x = label_to_float(fb, ncls_m1);
+        }
+        xs[ul] = x;
       }
       group_sync<GROUPS, NT>(grp);
       const float* wAx = Wb + M.oA_x; const float* bA = Wb + M.oA_b; const float* bhh = Wb + M.obhh1;
@@ -538,26 +572,49 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
       if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(0);
-    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
-    PROF_MARK(1);
+    constexpr bool kEarlyHH = kSplit >= 2;                    // GRU-2's W_hh pass reads only h2(t-1): it need not wait for x1
+    if constexpr (kEarlyHH) {
+      grid_arrive<GROUPS, NT>(bar_ctr, grp, tid);
+      ++nbar;
+    } else {
+      if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid, s_ok)) return;
+      PROF_MARK(1);
+    }
 
     // ================= P2: GRU 2 =================
     for (int tb = tb_lo; tb < tb_hi; tb += BT) {
+      const bool first_tile = (tb == tb_lo);
       if constexpr (MT::kWide) {
         Gemm gi{}, gh{};
         gi.W = Wb + M.oih2; gi.ldw = M.ldX; gi.nseg = 2; gi.seg[0] = Seg{A.x1, R / 4};
         gi.seg[1] = Seg{auxT + (size_t)AUX * Bp, AUX / 4};
         gh.W = Wb + M.ohh2; gh.ldw = R; gh.nseg = 1; gh.seg[0] = Seg{h2c, R / 4};
+        if constexpr (kEarlyHH) {
+          // warps [0, NWG/2) own the W_ih GEMM (x1 from the other CTAs): only they wait; the W_hh warps start at once
+          if (first_tile && warp < NWG / 2) {
+            grid_wait_sub<NT / 2>(bar_ctr, nbar * ncta, A.error, grp, tid, s_ok);
+            PROF_MARK(1);
+          }
+        }
         wide_partials<NWG, U, UW, 3 * kUPC, 2, MT::RS2>(part, gi, gh, tb, Bp, warp, lane);
       } else {
-        stage_rows<NT>(stA, A.x1, R * G, tid);
         stage_rows<NT>(stA + R * G, auxT + (size_t)AUX * Bp, AUX * G, tid);
         stage_rows<NT>(stB, h2c, R * G, tid);
+        if constexpr (kEarlyHH) {
+          if (first_tile) {
+            if (!grid_wait<GROUPS, NT>(bar_ctr, nbar * ncta, A.error, grp, tid, s_ok)) return;
+            PROF_MARK(1);
+          }
+        }
+        stage_rows<NT>(stA, A.x1, R * G, tid);
         group_sync<GROUPS, NT>(grp);
         narrow_rows<G, 3>(nout, 0, Wb + M.oih2, M.ldX, stA, M.ldX / 4, 3 * kUPC, 0, NWG / 2, warp, lane);
         narrow_rows<G, 3>(nout, 1, Wb + M.ohh2, R, stB, R / 4, 3 * kUPC, NWG / 2, NWG / 2, warp, lane);
       }
       group_sync<GROUPS, NT>(grp);
+      if constexpr (kEarlyHH && MT::kWide) {
+        if (first_tile && !s_ok[grp]) return;       // the sub-group wait timed out: every thread of the group leaves here
+      }
       const float* bih = Wb + M.obih2; const float* bhh = Wb + M.obhh2;
       for (int idx = tid; idx < BT * kUPC; idx += NT) {
         const int ul = idx % BT, j = idx / BT;
@@ -577,7 +634,7 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
       if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(4);
-    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
+    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid, s_ok)) return;
     PROF_MARK(5);
 
     // ================= P3: fc1 + relu  (CTA 0 also recycles the argmax slot the NEXT step will use) =================
@@ -604,7 +661,7 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
       if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(6);
-    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
+    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid, s_ok)) return;
     PROF_MARK(7);
 
     // ================= P4: fc2 + relu =================
@@ -629,7 +686,7 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
       if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(8);
-    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
+    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid, s_ok)) return;
     PROF_MARK(9);
 
     // ================= P5: fc3 + distributed Gumbel-max sampling =================
@@ -674,9 +731,16 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
       if (tb + BT < tb_hi) group_sync<GROUPS, NT>(grp);
     }
     PROF_MARK(10);
-    if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid)) return;
-    PROF_MARK(11);
+    if constexpr (kSplit >= 1) {                      // the wait sits in the next step's P01, after its GEMMs
+      grid_arrive<GROUPS, NT>(bar_ctr, grp, tid);
+      pend_target = (++nbar) * ncta;
+      pending = true;
+    } else {
+      if (!grid_barrier<GROUPS, NT>(bar_ctr, (++nbar) * ncta, A.error, grp, tid, s_ok)) return;
+      PROF_MARK(11);
+    }
   }
+  if (pending && !grid_wait<GROUPS, NT>(bar_ctr, pend_target, A.error, grp, tid, s_ok)) return;
   if (A.prof && grp == 0 && tid == 0)
     for (int i = 0; i < 12; ++i) A.prof[(size_t)c * 12 + i] = pf[i];
 #undef PROF_MARK
