@@ -567,7 +567,8 @@ static void launch_grid_t(b200tts_wavernn* ctx, GridArgs& a, cudaStream_t st) {
 enum { GV_N4, GV_N8, GV_W1, GV_W1x2, GV_W2x2, GV_W4x2, GV_W2, GV_W4, GV_W2_2x2 };
 static int grid_variant(int B, int* variant) {
   if (B <= 4) { *variant = GV_N4; return 4; }
-  if (B <= 8) { *variant = GV_N8; return 8; }
+  static const bool narrow8 = getenv("B200TTS_GRID_NARROW8") != nullptr;       // A/B switch: measured 30.7 us/step against 29.4 us
+  if (B <= 8 && narrow8) { *variant = GV_N8; return 8; }                       // for the 32-wide mapping, so 5..8 utterances go wide
   if (B <= 32) { *variant = GV_W1; return 32; }
   static const bool mid_dual = getenv("B200TTS_GRID_MID_DUAL") != nullptr;       // A/B switch: old mid-batch mapping
   if (B <= 64) { *variant = mid_dual ? GV_W1x2 : GV_W2; return 64; }
