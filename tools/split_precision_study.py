@@ -51,7 +51,7 @@ class Weight:
         self.w = np.asarray(w, dtype=F32)
         self.mode, self.transposed = mode, transposed
         self.dtype, self.shape, self.ndim = self.w.dtype, self.w.shape, self.w.ndim
-        drop, parts = {'bf16': (16, 1), 'bf16x3_6': (16, 3), 'bf16x3_9': (16, 3), 'tf32': (13, 1), 'tf32x3': (13, 2)}.get(
+        drop, parts = {'bf16': (16, 1), 'bf16x2': (16, 2), 'bf16x3_6': (16, 3), 'bf16x3_9': (16, 3), 'tf32': (13, 1), 'tf32x3': (13, 2)}.get(
             mode, (0, 0))
         self.drop, self.nparts = drop, parts
         self.parts = [np.ascontiguousarray(p.T) for p in split(self.w, drop, parts)] if parts else None
@@ -80,7 +80,7 @@ class Weight:
         n = self.nparts
         if self.mode == 'bf16x3_6':
             terms = [(i, j) for i in range(n) for j in range(n) if i + j <= 2]
-        elif self.mode == 'tf32x3':
+        elif self.mode in ('tf32x3', 'bf16x2'):
             terms = [(0, 0), (0, 1), (1, 0)]
         else:
             terms = [(i, j) for i in range(n) for j in range(n)]
@@ -105,10 +105,10 @@ def first_diff(a, b):
     return int(d.min()) if d.size else None
 
 
-def study(name, params, mels, steps, seed):
+def study(name, params, mels, steps, seed, modes):
     print(f'== {name}: {mels.shape[0]} utterance(s), {steps} steps, shared noise seed {seed}')
     ref = None
-    for mode in ('fp32', 'fp64', 'bf16x3_9', 'bf16x3_6', 'tf32x3', 'tf32', 'bf16'):
+    for mode in modes:
         t0 = time.time()
         lab = wo.generate(wrap(params, mode), mels, seed=seed, max_steps=steps)['labels']
         if ref is None:
@@ -123,15 +123,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=22000)
     ap.add_argument('--utterances', type=int, default=4)
+    ap.add_argument('--modes', default='fp32,fp64,bf16x3_9,bf16x3_6,tf32x3,tf32,bf16', help='first entry is the comparison base')
+    ap.add_argument('--skip-synth', action='store_true')
     ap.add_argument('--ckpt', default=os.path.join(ROOT, 'oracle', '_ref', 'latest_weights.pyt'))
     a = ap.parse_args()
     frames = (a.steps + 274) // 275 + 1
     mels = synth.synth_mels(1, a.utterances, max(frames, 21))
-    study('synthetic weights (synth_state_dict(0))', wo.as_params(synth.synth_state_dict(0)), mels, a.steps, 7)
+    modes = a.modes.split(',')
+    if not a.skip_synth:
+        study('synthetic weights (synth_state_dict(0))', wo.as_params(synth.synth_state_dict(0)), mels, a.steps, 7, modes)
     if os.path.isfile(a.ckpt):
         import torch
         sd = torch.load(a.ckpt, map_location='cpu', weights_only=False)
-        study('shipped checkpoint', wo.as_params(sd), mels, a.steps, 7)
+        study('shipped checkpoint', wo.as_params(sd), mels, a.steps, 7, modes)
 
 
 if __name__ == '__main__':
