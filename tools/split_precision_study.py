@@ -57,6 +57,7 @@ class Weight:
         self.parts = [np.ascontiguousarray(p.T) for p in split(self.w, drop, parts)] if parts else None
         self.wT64 = np.ascontiguousarray(self.w.T.astype(np.float64)) if mode == 'fp64' else None
         self.wT = np.ascontiguousarray(self.w.T)
+        self.rng = np.random.RandomState(abs(hash(mode)) % (2 ** 31))
 
     def astype(self, _):
         return self
@@ -74,6 +75,10 @@ class Weight:
         assert self.transposed
         if self.mode == 'fp32':
             return x @ self.wT
+        if self.mode.startswith('noise'):          # fp32 result + gaussian error of sigma * max|result| (a stand-in for
+            y = x @ self.wT                        # an accumulator that is less exact than IEEE fp32, e.g. the tensor core's)
+            sigma = float(self.mode[5:])
+            return (y + self.rng.standard_normal(y.shape).astype(F32) * F32(sigma * np.abs(y).max())).astype(F32)
         if self.mode == 'fp64':
             return (x.astype(np.float64) @ self.wT64).astype(F32)
         xs = split(x, self.drop, self.nparts)
