@@ -1,14 +1,20 @@
 """CPU oracle for the Tacotron-2 forward-attention inference path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-*** PARITY UNPINNED ***  The reference runs on TensorFlow 1.14 (`tf.contrib.*`), which is not installable here and
+The reference runs on TensorFlow 1.14 (`tf.contrib.*`), which is not installable here and
 the reference ships no tests / golden mels for this path.  This is therefore a numpy (float32)
 restatement written from the reference's source plus the documented semantics of the TF 1.14 ops it calls
 (`tf.nn.rnn_cell.LSTMCell`: gates i,j,f,o, forget_bias 1.0, kernel [in+units, 4*units]; `tf.layers.batch_normalization`
 epsilon 1e-3 with moving statistics; `tf.layers.conv1d` 'same' cross-correlation with kernel [k,in,out];
 `tf.layers.dropout` keep-scaling; `BahdanauAttention` bias-free memory/query layers, -inf score masking, softmax).
-Weak pins that ARE checked (tests/test_tacotron_oracle.py): variable names/shapes of the shipped checkpoint, and that on a
-real training sentence (train.txt line 241, 444 ground-truth frames) the decoder attends monotonically and its stop token
-fires near the ground-truth length.
+*** NUMERIC parity unpinned, STRUCTURE pinned. ***  Pins that ARE checked:
+  * tests/test_tacotron_graph_pins.py: every assumption about TF-internal arithmetic (GRAPH_ASSUMPTIONS below: LSTM gate
+    order / forget bias / concat order, zoneout and which h is passed on, prenet dropout rate and scaling, batch-norm
+    epsilon, the forward-attention step's op sequence, what is cumulated, what feeds the location convolution, the 1e-10,
+    the -inf mask, the operand order of every concat, the clip range) against tests/golden/taco_graph_facts.json, which
+    oracle/make_golden_taco_graph.py read out of the reference's own serialized graph (`tacotron_model.ckpt-206500.meta`);
+  * tests/test_tacotron_oracle.py: variable names/shapes of the shipped checkpoint, and that on a real training sentence
+    (train.txt line 241, 444 ground-truth frames) the decoder attends monotonically and its stop token fires near the
+    ground-truth length.
 
 Only tests/, __graft_entry__.smoke() and bench.py may import this module.  Reference citations are relative to the
 reference root.
@@ -20,12 +26,34 @@ import numpy as np
 F32 = np.float32
 P = 'decoder/'
 
+# Everything this restatement assumes about arithmetic that lives in TensorFlow 1.14 rather than in the reference's own
+# files.  The functions below take their constants from this table, and tests/test_tacotron_graph_pins.py compares the table
+# with tests/golden/taco_graph_facts.json -- facts read out of the reference's serialized graph (`*.meta` next to the
+# shipped checkpoint) by oracle/make_golden_taco_graph.py.  The numeric outputs remain unpinned (header), the structure
+# is pinned.
+GRAPH_ASSUMPTIONS = {
+    'lstm_gate_order': ['i', 'j', 'f', 'o'],        # np.split order in lstm_cell
+    'lstm_forget_bias': 1.0,
+    'lstm_kernel_input_order': ['x', 'h'],          # concat([x, h]) @ kernel
+    'zoneout': 0.1,                                 # both cell and hidden state, encoder and decoder
+    'cell_output_is_unzoned_h': True,
+    'batch_norm_epsilon': 1e-3,
+    'prenet_dropout_rate': 0.5,                     # keep-mask scaled by 1 / (1 - rate)
+    'attention_forward_epsilon': 1e-10,
+    'attention_cumulates': 'softmax',               # cum += softmax output BEFORE the forward modulation
+    'attention_location_input': 'cumulated',
+    'attention_mu_dense_input': ['context', 'h2'],
+    'projection_input': ['h2', 'context'],
+    'lstm_input': ['prenet', 'prev_context'],
+    'output_clip': [-4.1, 4.0],
+}
+
 
 def _sigmoid(x):
     return (F32(1) / (F32(1) + np.exp(-x, dtype=F32))).astype(F32)
 
 
-def lstm_cell(x, c, h, kernel, bias, forget_bias=1.0):
+def lstm_cell(x, c, h, kernel, bias, forget_bias=GRAPH_ASSUMPTIONS['lstm_forget_bias']):
     """tf.nn.rnn_cell.LSTMCell step (used at tacotron/models/modules.py:100,118): returns (new_c, new_h)."""
     z = (np.concatenate([x, h], axis=-1) @ kernel + bias).astype(F32)
     i, j, f, o = np.split(z, 4, axis=-1)
@@ -34,7 +62,7 @@ def lstm_cell(x, c, h, kernel, bias, forget_bias=1.0):
     return new_c, new_h
 
 
-def zoneout_lstm(x, c, h, kernel, bias, zoneout=0.1):
+def zoneout_lstm(x, c, h, kernel, bias, zoneout=GRAPH_ASSUMPTIONS['zoneout']):
     """ZoneoutLSTMCell.__call__ at inference, modules.py:114-142: the OUTPUT is the un-zoned new_h (:118,:142), the
     carried state is (1-z)*new + z*prev (:137-138)."""
     new_c, new_h = lstm_cell(x, c, h, kernel, bias)
@@ -56,7 +84,7 @@ def conv1d_same(x, kernel, bias):
     return (y + bias).astype(F32)
 
 
-def batch_norm(x, w, prefix, eps=1e-3):
+def batch_norm(x, w, prefix, eps=GRAPH_ASSUMPTIONS['batch_norm_epsilon']):
     """tf.layers.batch_normalization(training=False): moving statistics, epsilon 1e-3 (modules.py:388)."""
     g, b = w[prefix + '/gamma'], w[prefix + '/beta']
     m, v = w[prefix + '/moving_mean'], w[prefix + '/moving_variance']
@@ -99,7 +127,7 @@ def location_features(w, cum):
     return (f @ w[P + 'Location_Sensitive_Attention/location_features_layer/kernel']).astype(F32)   # [Tx, 128]
 
 
-def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, zoneout=0.1):
+def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, zoneout=GRAPH_ASSUMPTIONS['zoneout']):
     """The decoder while-loop for ONE sentence: dynamic_decode(CustomDecoder(TacotronDecoderCell, TacoTestHelper))
     (tacotron.py:99-103; custom_decoder.py:105-135; helpers.py:36-66; Architecture_wrappers.py:175-218;
     attention.py:119-231; `window=True` adds forward_attention.py:171-215).
@@ -129,13 +157,13 @@ def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, 
     frames, stops, aligns, masks = [], [], [], []
     for step in range(max_iters):
         # -- prenet, dropout always on (modules.py:240-251)
-        m = dropout_masks[step] if dropout_masks is not None else (rs.uniform(size=(2, 256)) >= 0.5)
+        m = dropout_masks[step] if dropout_masks is not None else (rs.uniform(size=(2, 256)) >= GRAPH_ASSUMPTIONS['prenet_dropout_rate'])
         m = np.asarray(m, dtype=F32)
         masks.append(m)
         p = x
         for li in (1, 2):
             p = np.maximum((p @ w[P + f'decoder_prenet/dense_{li}/kernel'] + w[P + f'decoder_prenet/dense_{li}/bias']).astype(F32), 0)
-            p = (p * m[li - 1] * F32(2.0)).astype(F32)                                       # keep-prob 0.5 scaling
+            p = (p * m[li - 1] * F32(1.0 / (1.0 - GRAPH_ASSUMPTIONS['prenet_dropout_rate']))).astype(F32)   # 1/(1-rate)
         # -- 2 x zoneout LSTM (Architecture_wrappers.py:180-183)
         o1, c1, h1 = zoneout_lstm(np.concatenate([p, ctx], axis=1), c1, h1, k1, b1, zoneout)
         o2, c2, h2 = zoneout_lstm(o1, c2, h2, k2, b2, zoneout)
@@ -147,7 +175,7 @@ def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, 
         a = (e / e.sum(dtype=F32)).astype(F32)                                               # softmax (probability_fn)
         cum = (cum + a).astype(F32)                                                          # :154 (pre-modulation)
         shift = np.concatenate([[F32(0)], alpha[:-1]]).astype(F32)
-        al = (((F32(1) - mu) * alpha + mu * shift + F32(1e-10)) * a).astype(F32)             # :167
+        al = (((F32(1) - mu) * alpha + mu * shift + F32(GRAPH_ASSUMPTIONS['attention_forward_epsilon'])) * a).astype(F32)   # :167
         new_max = int(np.argmax(al))
         if window:                                                                           # forward_attention.py:171-215
             new_max = max_att if new_max <= max_att else max_att + 1
@@ -188,7 +216,7 @@ def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, 
 def postnet(w, dec):
     """Clip (tacotron.py:111-112) -> 5 x conv k5 (tanh x4, linear) -> BN (modules.py:368-376) -> projection -> residual add
     -> clip (tacotron.py:115-129).  dec [n,80] -> mel [n,80]."""
-    lo, hi = F32(-4.0 - 0.1), F32(4.0)
+    lo, hi = F32(GRAPH_ASSUMPTIONS['output_clip'][0]), F32(GRAPH_ASSUMPTIONS['output_clip'][1])
     d = np.clip(dec, lo, hi).astype(F32)
     x = d
     for i in (1, 2, 3, 4):
