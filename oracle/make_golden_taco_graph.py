@@ -205,6 +205,27 @@ def prenet_facts(nodes):
     return out
 
 
+def conv_block_facts(nodes):
+    """Per conv block: what sits between the convolution and the batch norm, and the convolution's padding."""
+    out = {}
+    blocks = [f'encoder_convolutions/conv_layer_{i}_encoder_convolutions/' for i in (1, 2, 3)] + \
+             [f'postnet_convolutions/conv_layer_{i}_postnet_convolutions/' for i in (1, 2, 3, 4, 5)]
+    for b in blocks:
+        bn_in = nodes[P + b + 'batch_normalization/batchnorm/mul_1']['input'][0]
+        op = nodes[bn_in]['op']
+        conv = nodes[P + b + 'conv1d/conv1d']
+        out[b.split('/')[1]] = {
+            'before_batch_norm': op if op in ('Relu', 'Tanh') else 'linear',
+            'bias_before_activation': nodes[P + b + 'conv1d/BiasAdd']['input'][0].endswith('conv1d/conv1d/Squeeze'),
+            'padding': conv['attr']['padding'].split(b'\x04', 1)[1].decode(),
+            'scale_is_gamma_rsqrt_var_plus_eps': nodes[P + b + 'batch_normalization/batchnorm/Rsqrt']['input'][0].endswith('batchnorm/add')
+            and nodes[P + b + 'batch_normalization/batchnorm/mul']['input'][1].endswith('gamma/read'),
+        }
+    loc = nodes[STEP + 'Location_Sensitive_Attention/location_features_convolution/conv1d']
+    out['location_features_convolution'] = {'padding': loc['attr']['padding'].split(b'\x04', 1)[1].decode()}
+    return out
+
+
 def collect(meta_path):
     nodes = load_graph(meta_path)
     cell = STEP + 'decoder_LSTM/decoder_LSTM/multi_rnn_cell/'
@@ -219,6 +240,7 @@ def collect(meta_path):
         'encoder_lstm_fw': lstm_facts(nodes, P + 'encoder_LSTM/bidirectional_rnn/fw/fw/while/', 'encoder_fw_LSTM'),
         'encoder_lstm_bw': lstm_facts(nodes, P + 'encoder_LSTM/bidirectional_rnn/bw/bw/while/', 'encoder_bw_LSTM'),
         'prenet': prenet_facts(nodes),
+        'conv_blocks': conv_block_facts(nodes),
         'attention': attention_facts(nodes),
         'batch_norm_epsilon': sorted({round(const_float(nodes, n), 9) for n in bn}),
         'batch_norm_layers': len(bn),
@@ -249,7 +271,7 @@ def main():
     with open(a.out, 'w') as f:
         json.dump(facts, f, indent=1, sort_keys=True)
         f.write('\n')
-    print(json.dumps(facts, indent=1, sort_keys=True))
+    print(f'wrote {a.out}: {len(json.dumps(facts))} bytes, keys {sorted(facts)}')
 
 
 if __name__ == '__main__':

@@ -89,3 +89,17 @@ def test_attention_step_wiring(facts):
     assert a['projection_input'] == A['projection_input']
     assert a['lstm_input'] == A['lstm_input']
     assert a['frame_and_stop_share_input']
+
+
+def test_conv_blocks(facts):
+    """conv('same') + bias -> activation -> batch norm, as conv_block() in the oracle (modules.py:379-391)."""
+    cb = facts['conv_blocks']
+    for i in (1, 2, 3):
+        assert cb[f'conv_layer_{i}_encoder_convolutions']['before_batch_norm'] == 'Relu'
+    for i in (1, 2, 3, 4):
+        assert cb[f'conv_layer_{i}_postnet_convolutions']['before_batch_norm'] == 'Tanh'
+    assert cb['conv_layer_5_postnet_convolutions']['before_batch_norm'] == 'linear'
+    for k, v in cb.items():
+        assert v['padding'] == 'SAME', k
+        if k != 'location_features_convolution':
+            assert v['bias_before_activation'] and v['scale_is_gamma_rsqrt_var_plus_eps'], k
