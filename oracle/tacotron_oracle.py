@@ -6,7 +6,13 @@ restatement written from the reference's source plus the documented semantics of
 (`tf.nn.rnn_cell.LSTMCell`: gates i,j,f,o, forget_bias 1.0, kernel [in+units, 4*units]; `tf.layers.batch_normalization`
 epsilon 1e-3 with moving statistics; `tf.layers.conv1d` 'same' cross-correlation with kernel [k,in,out];
 `tf.layers.dropout` keep-scaling; `BahdanauAttention` bias-free memory/query layers, -inf score masking, softmax).
-*** NUMERIC parity unpinned, STRUCTURE pinned. ***  Pins that ARE checked:
+*** Pinning status: the DECODER STEP (rows a-7, a-8 of SURVEY section 8: prenet, both LSTM cells, forward attention,
+projections) is pinned numerically AND structurally against the reference's own serialized graph; whole-utterance TF
+outputs, the encoder and the postnet have no reference vectors (numerically unpinned). ***  Pins that ARE checked:
+  * tests/test_tacotron_step_pins.py: `decoder_step` reproduces (to 1e-6; measured 0.0) every intermediate obtained by
+    EXECUTING the `CustomDecoderStep` sub-graph of `tacotron_model.ckpt-206500.meta` with a numpy op interpreter
+    (oracle/tf_graph_eval.py) on the shipped weights, for five loop states of a real sentence
+    (oracle/make_golden_taco_step.py -> tests/golden/taco_step_from_graph.npz);
   * tests/test_tacotron_graph_pins.py: every assumption about TF-internal arithmetic (GRAPH_ASSUMPTIONS below: LSTM gate
     order / forget bias / concat order, zoneout and which h is passed on, prenet dropout rate and scaling, batch-norm
     epsilon, the forward-attention step's op sequence, what is cumulated, what feeds the location convolution, the 1e-10,
@@ -127,17 +133,17 @@ def location_features(w, cum):
     return (f @ w[P + 'Location_Sensitive_Attention/location_features_layer/kernel']).astype(F32)   # [Tx, 128]
 
 
-def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, zoneout=GRAPH_ASSUMPTIONS['zoneout']):
-    """The decoder while-loop for ONE sentence: dynamic_decode(CustomDecoder(TacotronDecoderCell, TacoTestHelper))
-    (tacotron.py:99-103; custom_decoder.py:105-135; helpers.py:36-66; Architecture_wrappers.py:175-218;
-    attention.py:119-231; `window=True` adds forward_attention.py:171-215).
+def decoder_step(w, memory, keys, x, m, st, zoneout=GRAPH_ASSUMPTIONS['zoneout'], modulate=None):
+    """ONE iteration of the decoder loop: TacotronDecoderCell.__call__ (Architecture_wrappers.py:175-218) with
+    Prenet (modules.py:240-251), 2 x ZoneoutLSTMCell (:114-142), ForwardLocationSensitiveAttention.__call__
+    (attention.py:119-231) and the two projections (modules.py:304,334-342).
 
-    memory [Tx, 512]; dropout_masks optional [steps, 2, 256] of {0,1} keep flags for the two prenet layers
-    (drawn from RandomState(seed) when None; prenet dropout is ON at inference, modules.py:249).
-    Returns dict(frames [n,80] raw decoder outputs, stop [n], alignments [n,Tx], n_steps, masks).
+    x [1,80] previous frame; m [2,256] prenet keep flags; st = dict(c1,h1,c2,h2 [1,256], ctx [1,512], alpha, cum [Tx], mu);
+    `modulate(al) -> al` lets decode() apply the optional inference window before the normalisation.
+    Returns (intermediates, new state).  tests/test_tacotron_step_pins.py checks the intermediates against the reference's
+    own serialized decoder-step graph executed on the shipped weights (oracle/make_golden_taco_step.py).
     """
-    Tx = memory.shape[0]
-    keys = (memory @ w['memory_layer/kernel']).astype(F32)                                   # BahdanauAttention ctor
+    A = GRAPH_ASSUMPTIONS
     Wq = w[P + 'Location_Sensitive_Attention/query_layer/kernel']
     v_a = w[P + 'Location_Sensitive_Attention/attention_variable_projection']
     b_a = w[P + 'Location_Sensitive_Attention/attention_bias']
@@ -145,72 +151,102 @@ def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, 
     b1 = w[P + 'decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/bias']
     k2 = w[P + 'decoder_LSTM/multi_rnn_cell/cell_1/decoder_LSTM_2/kernel']
     b2 = w[P + 'decoder_LSTM/multi_rnn_cell/cell_1/decoder_LSTM_2/bias']
-    U = k1.shape[1] // 4
+    z = F32(zoneout)
+    # -- prenet, dropout always on (modules.py:240-251)
+    p = x
+    for li in (1, 2):
+        p = np.maximum((p @ w[P + f'decoder_prenet/dense_{li}/kernel'] + w[P + f'decoder_prenet/dense_{li}/bias']).astype(F32), 0)
+        p = (p * m[li - 1] * F32(1.0 / (1.0 - A['prenet_dropout_rate']))).astype(F32)       # keep-scaling 1/(1-rate)
+    # -- 2 x zoneout LSTM (Architecture_wrappers.py:180-183): the un-zoned h goes on, the zoned pair is the carried state
+    nc1, nh1 = lstm_cell(np.concatenate([p, st['ctx']], axis=1), st['c1'], st['h1'], k1, b1)
+    nc2, nh2 = lstm_cell(nh1, st['c2'], st['h2'], k2, b2)
+    zoned = lambda new, prev: ((F32(1) - z) * new + z * prev).astype(F32)                    # modules.py:137-138
+    # -- attention (attention.py:132-167)
+    q = (nh2 @ Wq).astype(F32)                                                               # [1,128]
+    loc = location_features(w, st['cum'])
+    energy = (np.tanh(keys + q + loc + b_a, dtype=F32) * v_a).sum(axis=1).astype(F32)        # [Tx]
+    e = np.exp(energy - energy.max(), dtype=F32)
+    a = (e / e.sum(dtype=F32)).astype(F32)                                                   # softmax (probability_fn)
+    cum = (st['cum'] + a).astype(F32)                                                        # :154 (pre-modulation)
+    shift = np.concatenate([[F32(0)], st['alpha'][:-1]]).astype(F32)
+    al_raw = (((F32(1) - st['mu']) * st['alpha'] + st['mu'] * shift + F32(A['attention_forward_epsilon'])) * a).astype(F32)   # :167
+    al = modulate(al_raw) if modulate is not None else al_raw
+    al = (al / al.sum(dtype=F32)).astype(F32)                                                # :220
+    ctx = (al[None, :] @ memory).astype(F32)                                                 # :222
+    mu = _sigmoid((np.concatenate([ctx, nh2], axis=1) @ w[P + 'dense/kernel'] + w[P + 'dense/bias']).astype(F32))[0, 0]
+    # -- projections (Architecture_wrappers.py:196-199)
+    pin = np.concatenate([nh2, ctx], axis=1)
+    frame = (pin @ w[P + 'linear_transform_projection/projection_linear_transform_projection/kernel']
+             + w[P + 'linear_transform_projection/projection_linear_transform_projection/bias']).astype(F32)
+    stop_logit = (pin @ w[P + 'stop_token_projection/projection_stop_token_projection/kernel']
+                  + w[P + 'stop_token_projection/projection_stop_token_projection/bias']).astype(F32)
+    out = dict(prenet=p, new_c1=nc1, new_h1=nh1, new_c2=nc2, new_h2=nh2, query=q, energy=energy, softmax=a, cum=cum,
+               forward_raw=al_raw, alignments=al, context=ctx, mu=mu, frame=frame, stop_logit=stop_logit)
+    new = dict(c1=zoned(nc1, st['c1']), h1=zoned(nh1, st['h1']), c2=zoned(nc2, st['c2']), h2=zoned(nh2, st['h2']),
+               ctx=ctx, alpha=al, cum=cum, mu=mu)
+    return out, new
+
+
+def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, zoneout=GRAPH_ASSUMPTIONS['zoneout'],
+           capture_states=()):
+    """The decoder while-loop for ONE sentence: dynamic_decode(CustomDecoder(TacotronDecoderCell, TacoTestHelper))
+    (tacotron.py:99-103; custom_decoder.py:105-135; helpers.py:36-66); `window=True` adds forward_attention.py:171-215.
+
+    memory [Tx, 512]; dropout_masks optional [steps, 2, 256] of {0,1} keep flags for the two prenet layers
+    (drawn from RandomState(seed) when None; prenet dropout is ON at inference, modules.py:249).
+    Returns dict(frames [n,80] raw decoder outputs, stop [n], alignments [n,Tx], n_steps, masks
+    [, states {step: (x, state)} for the steps listed in `capture_states`]).
+    """
+    Tx = memory.shape[0]
+    keys = (memory @ w['memory_layer/kernel']).astype(F32)                                   # BahdanauAttention ctor
+    U = w[P + 'decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/kernel'].shape[1] // 4
     rs = np.random.RandomState(seed)
-    c1 = h1 = c2 = h2 = np.zeros((1, U), dtype=F32)
-    ctx = np.zeros((1, memory.shape[1]), dtype=F32)                                          # zero_state attention (:164)
-    alpha = np.zeros(Tx, dtype=F32); alpha[0] = 1                                            # init_alpha (attention.py:112)
-    cum = alpha.copy()                                                                       # init_cumulated_alignments
-    mu = F32(0.5)                                                                            # init_mu
-    max_att, pos_rec = 0, 0
+    zeros = np.zeros((1, U), dtype=F32)
+    alpha0 = np.zeros(Tx, dtype=F32); alpha0[0] = 1                                          # init_alpha (attention.py:112)
+    st = dict(c1=zeros, h1=zeros, c2=zeros, h2=zeros,
+              ctx=np.zeros((1, memory.shape[1]), dtype=F32),                                 # zero_state attention (:164)
+              alpha=alpha0, cum=alpha0.copy(), mu=F32(0.5))                                  # init_cumulated_alignments, init_mu
+    win = dict(max_att=0, pos_rec=0)
     x = np.zeros((1, 80), dtype=F32)                                                         # _go_frames (helpers.py:149)
-    frames, stops, aligns, masks = [], [], [], []
+    frames, stops, aligns, masks, captured = [], [], [], [], {}
+
+    def window_modulate(al):                                                                 # forward_attention.py:171-215
+        max_att, pos_rec = win['max_att'], win['pos_rec']
+        new_max = int(np.argmax(al))
+        new_max = max_att if new_max <= max_att else max_att + 1
+        if pos_rec < 5 and 2 < new_max:
+            new_max = max_att
+        if new_max == max_att:
+            pos_rec = pos_rec + 1
+        else:
+            pos_rec = 1
+        if not pos_rec < 10:                                                                 # :191-195
+            new_max, pos_rec = new_max + 1, 1
+        idx = np.arange(Tx)
+        keep = (idx >= new_max - 2) & (idx < new_max + 3)
+        al = np.where(keep, al, F32(0)).astype(F32)
+        peak = idx == min(max(new_max, 0), Tx - 1)
+        tot = al.sum(dtype=F32)
+        tot = F32(1.0) if tot < F32(1e-10) else tot                                          # :209-213
+        al = np.where(peak & (idx < new_max + 1), tot * F32(2.0), al).astype(F32)            # :215
+        win['max_att'], win['pos_rec'] = new_max, pos_rec
+        return al
+
     for step in range(max_iters):
-        # -- prenet, dropout always on (modules.py:240-251)
         m = dropout_masks[step] if dropout_masks is not None else (rs.uniform(size=(2, 256)) >= GRAPH_ASSUMPTIONS['prenet_dropout_rate'])
         m = np.asarray(m, dtype=F32)
         masks.append(m)
-        p = x
-        for li in (1, 2):
-            p = np.maximum((p @ w[P + f'decoder_prenet/dense_{li}/kernel'] + w[P + f'decoder_prenet/dense_{li}/bias']).astype(F32), 0)
-            p = (p * m[li - 1] * F32(1.0 / (1.0 - GRAPH_ASSUMPTIONS['prenet_dropout_rate']))).astype(F32)   # 1/(1-rate)
-        # -- 2 x zoneout LSTM (Architecture_wrappers.py:180-183)
-        o1, c1, h1 = zoneout_lstm(np.concatenate([p, ctx], axis=1), c1, h1, k1, b1, zoneout)
-        o2, c2, h2 = zoneout_lstm(o1, c2, h2, k2, b2, zoneout)
-        # -- attention (attention.py:132-167)
-        q = (o2 @ Wq).astype(F32)                                                            # [1,128]
-        loc = location_features(w, cum)
-        energy = (np.tanh(keys + q + loc + b_a, dtype=F32) * v_a).sum(axis=1).astype(F32)    # [Tx]
-        e = np.exp(energy - energy.max(), dtype=F32)
-        a = (e / e.sum(dtype=F32)).astype(F32)                                               # softmax (probability_fn)
-        cum = (cum + a).astype(F32)                                                          # :154 (pre-modulation)
-        shift = np.concatenate([[F32(0)], alpha[:-1]]).astype(F32)
-        al = (((F32(1) - mu) * alpha + mu * shift + F32(GRAPH_ASSUMPTIONS['attention_forward_epsilon'])) * a).astype(F32)   # :167
-        new_max = int(np.argmax(al))
-        if window:                                                                           # forward_attention.py:171-215
-            new_max = max_att if new_max <= max_att else max_att + 1
-            if pos_rec < 5 and 2 < new_max:
-                new_max = max_att
-            if new_max == max_att:
-                pos_rec = pos_rec + 1
-            else:
-                pos_rec = 1
-            if not pos_rec < 10:                                                             # :191-195
-                new_max, pos_rec = new_max + 1, 1
-            idx = np.arange(Tx)
-            keep = (idx >= new_max - 2) & (idx < new_max + 3)
-            al = np.where(keep, al, F32(0)).astype(F32)
-            peak = idx == min(max(new_max, 0), Tx - 1)
-            tot = al.sum(dtype=F32)
-            tot = F32(1.0) if tot < F32(1e-10) else tot                                      # :209-213
-            al = np.where(peak & (idx < new_max + 1), tot * F32(2.0), al).astype(F32)        # :215
-        max_att = new_max
-        al = (al / al.sum(dtype=F32)).astype(F32)                                            # :220
-        ctx = (al[None, :] @ memory).astype(F32)                                             # :222
-        mu = _sigmoid((np.concatenate([ctx, o2], axis=1) @ w[P + 'dense/kernel'] + w[P + 'dense/bias']).astype(F32))[0, 0]
-        alpha = al
-        # -- projections (Architecture_wrappers.py:196-199)
-        pin = np.concatenate([o2, ctx], axis=1)
-        frame = (pin @ w[P + 'linear_transform_projection/projection_linear_transform_projection/kernel']
-                 + w[P + 'linear_transform_projection/projection_linear_transform_projection/bias']).astype(F32)
-        stop = _sigmoid((pin @ w[P + 'stop_token_projection/projection_stop_token_projection/kernel']
-                         + w[P + 'stop_token_projection/projection_stop_token_projection/bias']).astype(F32))[0, 0]
-        frames.append(frame[0]); stops.append(stop); aligns.append(al)
+        if step in capture_states:
+            captured[step] = (x.copy(), {k: np.array(v, copy=True) for k, v in st.items()}, m.copy())
+        out, st = decoder_step(w, memory, keys, x, m, st, zoneout, window_modulate if window else None)
+        frame = out['frame']
+        stop = _sigmoid(out['stop_logit'])[0, 0]
+        frames.append(frame[0]); stops.append(stop); aligns.append(out['alignments'])
         x = frame                                                                            # helpers.py:64 (r = 1)
         if stop > 0.5:                                                                       # tf.round, half-to-even (:45)
             break
     return dict(frames=np.stack(frames), stop=np.array(stops, dtype=F32), alignments=np.stack(aligns),
-                n_steps=len(frames), masks=np.stack(masks))
+                n_steps=len(frames), masks=np.stack(masks), states=captured)
 
 
 def postnet(w, dec):

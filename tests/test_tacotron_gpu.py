@@ -1,6 +1,6 @@
 """sm_100a Tacotron-2 decoder loop (taco_decoder_kernel, through the C ABI) against the oracle with shared dropout masks.
-The oracle itself is parity-UNPINNED against the TF reference (see oracle/tacotron_oracle.py); tolerance from the north
-star: mel within 1e-4 abs, identical stop step."""
+The oracle's decoder step is pinned against the reference's serialized graph (tests/test_tacotron_step_pins.py); whole-run
+TF outputs do not exist (see oracle/tacotron_oracle.py).  Tolerance from the north star: mel within 1e-4 abs, identical stop step."""
 import numpy as np
 import pytest
 
@@ -67,6 +67,14 @@ def test_decoder_vs_oracle_real_checkpoint_config4():
     assert err <= 3e-4, err          # 1e-4 holds to ~step 40; fp32 accumulation-order noise x weights up to 30 afterwards
     np.testing.assert_allclose(out['stop'].cpu().numpy()[0, :HORIZON], ref['stop'][:HORIZON], rtol=0, atol=1e-5)
     assert np.array_equal(al[:HORIZON].argmax(1), ref['alignments'][:HORIZON].argmax(1))
+    # the same sentence / masks as tests/golden/taco_step_from_graph.npz: frames and alignments the reference's own serialized
+    # decoder-step graph produces at steps 0, 1, 7 (oracle/make_golden_taco_step.py) -- the CUDA loop against the graph itself
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, 'taco_step_from_graph.npz'))
+    for s in (0, 1, 7):
+        assert np.abs(fr[s] - z[f's{s}_graph_frame'][0]).max() <= 1e-4, s
+        assert np.abs(al[s] - z[f's{s}_graph_alignments'][0]).max() <= 1e-4, s
     mel_gpu, mel_ref = to.postnet(w, fr[:HORIZON]), to.postnet(w, ref['frames'][:HORIZON])
     assert np.abs(fr[:40] - ref['frames'][:40]).max() <= 1e-4
     assert np.abs(mel_gpu[:HORIZON - 4] - mel_ref[:HORIZON - 4]).max() <= 3e-4
