@@ -239,6 +239,14 @@ def collect(meta_path):
         cell + 'cell_0/decoder_LSTM_1/mul_2' else 'other',
         'encoder_lstm_fw': lstm_facts(nodes, P + 'encoder_LSTM/bidirectional_rnn/fw/fw/while/', 'encoder_fw_LSTM'),
         'encoder_lstm_bw': lstm_facts(nodes, P + 'encoder_LSTM/bidirectional_rnn/bw/bw/while/', 'encoder_bw_LSTM'),
+        'encoder_bilstm': {
+            'bw_reads_reversed_conv_output': nodes[P + 'encoder_LSTM/bidirectional_rnn/bw/ReverseSequence']['input'][0].endswith(
+                'conv_layer_3_encoder_convolutions/dropout/mul_1'),
+            'bw_output_is_reversed_back': nodes[P + 'encoder_LSTM/ReverseSequence']['input'][0] ==
+            P + 'encoder_LSTM/bidirectional_rnn/bw/bw/transpose_1',
+            'memory_concat': ['fw' if '/fw/' in i else 'bw_reversed' if i.endswith('encoder_LSTM/ReverseSequence') else i
+                              for i in nodes[P + 'encoder_LSTM/concat']['input'][:2]],
+        },
         'prenet': prenet_facts(nodes),
         'conv_blocks': conv_block_facts(nodes),
         'attention': attention_facts(nodes),

@@ -7,8 +7,12 @@ restatement written from the reference's source plus the documented semantics of
 epsilon 1e-3 with moving statistics; `tf.layers.conv1d` 'same' cross-correlation with kernel [k,in,out];
 `tf.layers.dropout` keep-scaling; `BahdanauAttention` bias-free memory/query layers, -inf score masking, softmax).
 *** Pinning status: the DECODER STEP (rows a-7, a-8 of SURVEY section 8: prenet, both LSTM cells, forward attention,
-projections) is pinned numerically AND structurally against the reference's own serialized graph; whole-utterance TF
-outputs, the encoder and the postnet have no reference vectors (numerically unpinned). ***  Pins that ARE checked:
+projections), the ENCODER (convolution blocks, single BiLSTM iterations, the fw/bw wiring) and the POSTNET are pinned
+numerically AND structurally against the reference's own serialized graph, executed op by op in numpy on the shipped
+weights.  What has no reference vectors: whole-utterance TensorFlow outputs (the decoder loop iterated, with TF's own
+random masks). ***  Pins that ARE checked:
+  * tests/test_tacotron_encpost_pins.py: encoder_convs / lstm_cell on the encoder kernels / postnet against the serialized
+    sub-graphs (oracle/make_golden_taco_encpost.py -> tests/golden/taco_encpost_from_graph.npz; 2e-7 relative);
   * tests/test_tacotron_step_pins.py: `decoder_step` reproduces (to 1e-6; measured 0.0) every intermediate obtained by
     EXECUTING the `CustomDecoderStep` sub-graph of `tacotron_model.ckpt-206500.meta` with a numpy op interpreter
     (oracle/tf_graph_eval.py) on the shipped weights, for five loop states of a real sentence
@@ -104,12 +108,21 @@ def conv_block(x, w, scope, activation):
     return batch_norm(y, w, scope + '/batch_normalization')
 
 
+def encoder_convs(w, ids):
+    """Embedding lookup (tacotron.py:44-47) and the 3 encoder convolution blocks (modules.py:168-174); returns the output of
+    every block, [Tx, 256] each (pinned against the serialized graph by tests/test_tacotron_encpost_pins.py)."""
+    x = w['inputs_embedding'][np.asarray(ids)].astype(F32)
+    outs = []
+    for i in (1, 2, 3):
+        x = conv_block(x, w, f'encoder_convolutions/conv_layer_{i}_encoder_convolutions', lambda v: np.maximum(v, F32(0)))
+        outs.append(x)
+    return outs
+
+
 def encoder(w, ids):
     """Embedding lookup (tacotron.py:44-47) -> 3 x conv k5/256 ReLU -> BN (modules.py:168-174) -> BiLSTM 2x256 with zoneout
     (modules.py:207-217).  ids: int [Tx].  Returns memory [Tx, 512]."""
-    x = w['inputs_embedding'][np.asarray(ids)].astype(F32)
-    for i in (1, 2, 3):
-        x = conv_block(x, w, f'encoder_convolutions/conv_layer_{i}_encoder_convolutions', lambda v: np.maximum(v, F32(0)))
+    x = encoder_convs(w, ids)[-1]
     Tx = x.shape[0]
     outs = []
     for direction, order in (('fw', range(Tx)), ('bw', range(Tx - 1, -1, -1))):

@@ -187,6 +187,12 @@ class Evaluator:
                 return (a * b).astype(np.result_type(a, b))
         if op == 'RealDiv':
             return (g(ins[0]) / g(ins[1])).astype(f32)
+        if op == 'Rsqrt':
+            return (f32(1) / np.sqrt(g(ins[0]), dtype=f32)).astype(f32)
+        if op == 'Maximum':
+            return np.maximum(g(ins[0]), g(ins[1]))
+        if op == 'Minimum':
+            return np.minimum(g(ins[0]), g(ins[1]))
         if op == 'Relu':
             return np.maximum(g(ins[0]), f32(0))
         if op == 'Sigmoid':

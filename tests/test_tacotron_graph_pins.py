@@ -103,3 +103,10 @@ def test_conv_blocks(facts):
         assert v['padding'] == 'SAME', k
         if k != 'location_features_convolution':
             assert v['bias_before_activation'] and v['scale_is_gamma_rsqrt_var_plus_eps'], k
+
+
+def test_encoder_bilstm_wiring(facts):
+    """memory = concat([forward outputs, backward outputs re-reversed]) as in oracle.encoder (modules.py:207-217)."""
+    e = facts['encoder_bilstm']
+    assert e['bw_reads_reversed_conv_output'] and e['bw_output_is_reversed_back']
+    assert e['memory_concat'] == ['fw', 'bw_reversed']
