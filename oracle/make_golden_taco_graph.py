@@ -3,8 +3,8 @@
 TEST INFRASTRUCTURE (like everything under oracle/): run HERE, where /root/reference exists; the result is the small
 fixture tests/golden/taco_graph_facts.json, which travels.
 
-TensorFlow 1.14 cannot run in this container, so oracle/tacotron_oracle.py has no numeric golden vectors ("parity
-unpinned").  What the reference does ship is `logs-Tacotron-2/taco_pretrained/tacotron_model.ckpt-206500.meta`, the
+TensorFlow 1.14 cannot run in this container, so oracle/tacotron_oracle.py cannot be compared with a TensorFlow run.
+What the reference does ship is `logs-Tacotron-2/taco_pretrained/tacotron_model.ckpt-206500.meta`, the
 MetaGraphDef written next to the checkpoint: the op-level graph that the reference's model code (tacotron/models/*.py)
 built.  It is the TRAINING graph (teacher-forcing helper, zoneout in its dropout form, batch statistics), but the LSTM
 cells, the attention step, the prenet and the projections are the same code in both modes.  This script walks that

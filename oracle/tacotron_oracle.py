@@ -39,8 +39,8 @@ P = 'decoder/'
 # Everything this restatement assumes about arithmetic that lives in TensorFlow 1.14 rather than in the reference's own
 # files.  The functions below take their constants from this table, and tests/test_tacotron_graph_pins.py compares the table
 # with tests/golden/taco_graph_facts.json -- facts read out of the reference's serialized graph (`*.meta` next to the
-# shipped checkpoint) by oracle/make_golden_taco_graph.py.  The numeric outputs remain unpinned (header), the structure
-# is pinned.
+# shipped checkpoint) by oracle/make_golden_taco_graph.py.  The numeric pins (the same graph EXECUTED in numpy) are
+# tests/test_tacotron_step_pins.py and tests/test_tacotron_encpost_pins.py.
 GRAPH_ASSUMPTIONS = {
     'lstm_gate_order': ['i', 'j', 'f', 'o'],        # np.split order in lstm_cell
     'lstm_forget_bias': 1.0,

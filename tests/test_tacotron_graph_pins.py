@@ -2,7 +2,7 @@
 
 tests/golden/taco_graph_facts.json was read out of `logs-Tacotron-2/taco_pretrained/tacotron_model.ckpt-206500.meta` (the
 MetaGraphDef the reference saved next to its checkpoint) by oracle/make_golden_taco_graph.py, without TensorFlow.  The
-oracle's numeric outputs stay unpinned (no TF here, no golden mels in the reference); what IS pinned here is every
+numeric pins are test_tacotron_step_pins.py / test_tacotron_encpost_pins.py (the same graph executed in numpy); what is pinned HERE is every
 assumption it makes about arithmetic that lives inside TensorFlow: gate order, forget bias, zoneout, dropout scaling,
 batch-norm epsilon, and the wiring of the forward-attention step.
 """

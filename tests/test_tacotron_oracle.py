@@ -1,4 +1,4 @@
-"""CPU checks of the Tacotron side: TF-bundle reader, and the weak structural pins of the (parity-unpinned) oracle."""
+"""CPU checks of the Tacotron side: TF-bundle reader, and whole-sentence behaviour of the oracle (its per-step arithmetic is pinned in test_tacotron_*_pins.py)."""
 import os
 
 import numpy as np
