@@ -96,9 +96,32 @@ class ClockSampler(threading.Thread):
 _BEST_THREADS = None
 
 
-def _pick_threads(wo, p, mels):
-    """The matvecs of one utterance are tiny (1536 x 512): more BLAS threads than ~8-16 only adds contention.  Probe a
-    few pool sizes on 150 steps each and keep the fastest -- "all the host threads it can USE"."""
+_CPU_CACHE = {}
+
+
+def _cpu_workload(batch):
+    """Weights + conditioning of the CPU arm, built once per process: `batch` utterances (the arm's own batch size, so the
+    host runs [batch x K] GEMMs like the reference's loop would on a [batch, 80, T] mel), minimum-length mels (21 frames:
+    the per-step cost does not depend on the utterance length), 8 distinct utterances tiled to `batch` rows (it does not
+    depend on the values either; the numpy conditioning network would otherwise take ~0.3 s per utterance)."""
+    if batch not in _CPU_CACHE:
+        from oracle import wavernn_oracle as wo
+        from tacotronv2_wavernn_chinese_b200 import synth
+        p = {k: (v.astype(np.float32) if v.dtype.kind == 'f' else v) for k, v in wo.as_params(synth.synth_state_dict(0)).items()}
+        distinct = min(8, batch)
+        mels = synth.synth_mels(1234, distinct, 21)
+        d = wo._dims(p)
+        mp = wo.pad_tensor(mels.transpose(0, 2, 1), d['pad'], 'both').transpose(0, 2, 1)
+        m_up, aux = wo.upsample(p, mp)
+        reps = (batch + distinct - 1) // distinct
+        tile = lambda a: np.ascontiguousarray(np.tile(a, (reps, 1, 1))[:batch])
+        _CPU_CACHE[batch] = (wo, p, tile(mels), (tile(m_up), tile(aux)))
+    return _CPU_CACHE[batch]
+
+
+def _pick_threads(batch):
+    """Probe a few BLAS pool sizes on the actual workload and keep the fastest -- "all the host threads it can USE"
+    (at batch 1 the matvecs are tiny and more than ~16 threads only adds contention; at batch 256 the GEMMs scale further)."""
     global _BEST_THREADS
     if _BEST_THREADS is not None:
         return _BEST_THREADS
@@ -108,64 +131,79 @@ def _pick_threads(wo, p, mels):
     except Exception:
         _BEST_THREADS = ncpu
         return ncpu
+    wo, p, mels, cond = _cpu_workload(batch)
+    n = 30 if batch > 1 else 150
     best, best_rate = 1, 0.0
-    for nt in sorted({1, 4, 8, 16, 32, ncpu} & set(range(1, ncpu + 1))):
+    for nt in sorted({1, 4, 8, 16, 32, 64, ncpu} & set(range(1, ncpu + 1))):
         with threadpool_limits(limits=nt):
-            wo.generate(p, mels, max_steps=20, seed=0)
-            r = wo.generate(p, mels, max_steps=150, seed=0)
-        rate = 150 / r['seconds']
+            wo.generate(p, mels, max_steps=3, seed=0, cond=cond)
+            r = wo.generate(p, mels, max_steps=n, seed=0, cond=cond)
+        rate = n / r['loop_seconds']
         if rate > best_rate:
             best, best_rate = nt, rate
     _BEST_THREADS = best
     return best
 
 
-def cpu_oracle_rate(frames, max_seconds=25.0):
-    """The reference algorithm (numpy oracle port, oracle/wavernn_oracle.py) on the host: one utterance, as many of
-    its T*hop steps as fit the time bound.  Returns (samples/s, steps run, threads used)."""
-    from oracle import wavernn_oracle as wo
-    from tacotronv2_wavernn_chinese_b200 import synth
+def cpu_oracle_rate(batch, max_seconds=25.0):
+    """The reference algorithm (numpy oracle port, oracle/wavernn_oracle.py) on the host cores, on the arm's batch size:
+    as many lock-steps of `batch` utterances as fit the time bound; the one-shot conditioning network is outside the timed
+    loop (see _cpu_workload).  Returns (samples/s, lock-steps run, threads used)."""
     import contextlib
-    p = wo.as_params(synth.synth_state_dict(0))
-    mels = synth.synth_mels(1234, 1, frames)
-    threads = _pick_threads(wo, p, mels)
+    wo, p, mels, cond = _cpu_workload(batch)
+    threads = _pick_threads(batch)
     try:
         from threadpoolctl import threadpool_limits
         ctx = threadpool_limits(limits=threads)
     except Exception:
         ctx = contextlib.nullcontext()
     with ctx:
-        probe = wo.generate(p, mels, max_steps=300, seed=0)      # includes the one-shot conditioning network
-        per_step = max(probe['seconds'] / 300, 1e-6)
-        steps = int(min(frames * HOP, max(300, max_seconds / per_step)))
-        r = wo.generate(p, mels, max_steps=steps, seed=0)
-    return steps / r['seconds'], steps, threads
+        probe = wo.generate(p, mels, max_steps=10, seed=0, cond=cond)
+        per_step = max(probe['loop_seconds'] / 10, 1e-6)
+        steps = int(min(mels.shape[2] * HOP, max(10, max_seconds / per_step)))
+        r = wo.generate(p, mels, max_steps=steps, seed=0, cond=cond)
+    return batch * steps / r['loop_seconds'], steps, threads
+
+
+def workload_config(args, N):
+    """The `config` object both arms print (BASELINE config 3)."""
+    B, T = args.batch, args.frames
+    return {'workload': f'BASELINE config 3: WaveRNN generate(), batch={B} utterances/GPU of {T}-frame synthetic '
+                        f'mels (voc_mode=RAW bits=10 hop=275), random-init weights of the shipped architecture',
+            'utterances_per_gpu': B, 'global_batch': N * B, 'frames': T, 'steps_per_utterance': T * HOP}
+
+
+def cpu_sample_text(batch, steps_run, frames):
+    return (f'{batch} utterances x {steps_run} of {frames * HOP} lock-steps per bench step, sampling loop only (the one-shot '
+            f'conditioning network is outside the timed region); numpy oracle port of generate(), fp32, BLAS threads chosen by probe')
 
 
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the host cores (the Python reference itself cannot travel to
-    the GPU box; this is the oracle port, pinned bit-for-bit to the reference's labels by tests/test_oracle_golden.py)."""
+    """--impl reference: the reference's algorithm on the host cores, on the b200 arm's workload (the Python reference itself
+    cannot travel to the GPU box; this is the oracle port, pinned bit-for-bit to the reference's labels by
+    tests/test_oracle_golden.py).  Each bench step is a time-bounded sample of the 22 000 lock-steps of the batch."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     per_step_budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     rates, steps_run, threads = [], 0, 1
     for i in range(args.warmup + args.steps):
-        rate, steps_run, threads = cpu_oracle_rate(args.frames, max_seconds=per_step_budget)
+        rate, steps_run, threads = cpu_oracle_rate(args.batch, max_seconds=per_step_budget)
         if i >= args.warmup:
             rates.append(rate)
     v = float(np.mean(rates))
-    sample = f'1 utterance x {steps_run} of {args.frames * HOP} steps per bench step (numpy oracle port, fp32)'
+    cfg = workload_config(args, 1)
+    cfg['parallelism'] = f'host CPU, {threads} BLAS threads (rank 0 only)'
     line = {
         'impl': 'reference', 'metric': 'wavernn_audio_samples_per_sec', 'value': v, 'unit': 'samples/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * steps_run / v,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * args.batch * steps_run / v,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'WaveRNN generate(), {args.frames}-frame synthetic mel, voc_mode=RAW bits=10 hop=275, CPU',
-                   'frames': args.frames},
-        'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'config': cfg,
+        'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+                         'sample': cpu_sample_text(args.batch, steps_run, args.frames)},
         'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-        'rtf': 22050.0 / v,
+        'rtf': 22050.0 / (v / args.batch),
     }
     print(json.dumps(line), flush=True)
 
@@ -282,11 +320,8 @@ def main():
             'metric': 'wavernn_audio_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': N,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'BASELINE config 3: WaveRNN generate(), batch={B} utterances/GPU of {T}-frame synthetic '
-                                   f'mels (voc_mode=RAW bits=10 hop=275), random-init weights of the shipped architecture',
-                       'utterances_per_gpu': B, 'global_batch': N * B, 'frames': T, 'steps_per_utterance': S,
-                       'kernel': args.kernel, 'l2': 'flushed between timed iterations (256 MiB fill)',
-                       'parallelism': f'utterance-sharded x{N}, NCCL all-gather of labels' if N > 1 else 'single GPU'},
+            'config': dict(workload_config(args, N), kernel=args.kernel, l2='flushed between timed iterations (256 MiB fill)',
+                           parallelism=f'utterance-sharded x{N}, NCCL all-gather of labels' if N > 1 else 'single GPU'),
             'rtf': 22050.0 / (value / (N * B)),
             'us_per_lockstep': 1e3 * gen_ms / S,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
@@ -301,9 +336,9 @@ def main():
             'e2e': e2e,
         }
         if not args.no_cpu_baseline and N == 1:        # reported baseline: rank 0, single-GPU runs only
-            rate, steps_run, threads = cpu_oracle_rate(T, max_seconds=15.0)
+            rate, steps_run, threads = cpu_oracle_rate(B, max_seconds=15.0)
             line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-                                    'sample': f'1 utterance x {steps_run} of {S} steps, numpy oracle port of generate()'}
+                                    'sample': cpu_sample_text(B, steps_run, T)}
         print(json.dumps(line), flush=True)
     if N > 1:
         dist.barrier()

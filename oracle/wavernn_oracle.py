@@ -203,14 +203,16 @@ def decode_mu_law(y, mu):
 # ----------------------------------------------------------------------------------------------
 # generate  (fatchord_version.py:169-264, unbatched branch)
 # ----------------------------------------------------------------------------------------------
-def generate(p, mels, q=None, teacher=None, keep_logits=None, mu_law=True, seed=0, max_steps=None):
+def generate(p, mels, q=None, teacher=None, keep_logits=None, mu_law=True, seed=0, max_steps=None, cond=None):
     """WaveRNN.generate restated for a batch of independent utterances.
 
     mels      [B, feat, T] float32 in [0,1]
     q         [S, B, ncls] Exp(1) noise; None -> drawn from numpy RandomState(seed)
     teacher   optional [B, S] labels fed back instead of the sampled ones
     keep_logits  None | 'all' | iterable of step indices -> logits kept for those steps
-    Returns dict(labels [B,S] int16, wave [B, wave_len] float64, logits {step: [B,ncls]}, seconds).
+    cond      optional (m_up [B,S,feat], aux [B,S,4*aux]) from a previous `upsample` call: skips the conditioning network
+              (bench.py's CPU arm times many short runs on the same conditioning)
+    Returns dict(labels [B,S] int16, wave [B, wave_len] float64, logits {step: [B,ncls]}, seconds, loop_seconds).
     The reference returns only utterance 0 (:253); this returns every row.
     """
     d = _dims(p)
@@ -220,8 +222,12 @@ def generate(p, mels, q=None, teacher=None, keep_logits=None, mu_law=True, seed=
     hop = d['hop']
     wave_len = (T - 1) * hop                                                                # :184
     t0 = time.perf_counter()
-    mp = pad_tensor(mels.transpose(0, 2, 1), d['pad'], 'both').transpose(0, 2, 1)           # :185
-    m_up, aux = upsample(pf, mp)                                                            # :186
+    if cond is None:
+        mp = pad_tensor(mels.transpose(0, 2, 1), d['pad'], 'both').transpose(0, 2, 1)       # :185
+        m_up, aux = upsample(pf, mp)                                                        # :186
+    else:
+        m_up, aux = cond
+    t_loop = time.perf_counter()
     S = m_up.shape[1] if max_steps is None else min(max_steps, m_up.shape[1])
     A = d['aux']
     h1 = np.zeros((B, d['rnn']), dtype=F32)                                                 # :194-196
@@ -244,8 +250,9 @@ def generate(p, mels, q=None, teacher=None, keep_logits=None, mu_law=True, seed=
         fb = teacher[:, i].astype(np.int64) if teacher is not None else lab
         x = label_to_float(fb, d['ncls'])[:, None]                                          # :235-237
     seconds = time.perf_counter() - t0
+    loop_seconds = time.perf_counter() - t_loop
     wave = finish_wave(labels, d['ncls'], wave_len, hop, mu_law) if S == m_up.shape[1] else None
-    return dict(labels=labels, wave=wave, logits=kept, seconds=seconds, steps=S)
+    return dict(labels=labels, wave=wave, logits=kept, seconds=seconds, loop_seconds=loop_seconds, steps=S)
 
 
 def fold_with_overlap(x, target, overlap):

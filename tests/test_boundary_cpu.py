@@ -186,3 +186,17 @@ def test_fold_geometry_matches_reference_formula():
         assert wo.fold_with_overlap(x, target, overlap).shape[:2] == (nf, target + 2 * overlap)
     assert lib.b200tts_wavernn_fold_geometry(2, 275, 100, 600, ctypes.byref(a), ctypes.byref(b)) != 0     # shorter than the overlap
     assert b'overlap' in lib.b200tts_last_error()
+
+
+def test_bench_cpu_arm_helpers():
+    """bench.py's CPU arm (cpu_baseline / --impl reference): same config object as the GPU arm, time-bounded batched sample."""
+    import argparse
+    import bench
+    args = argparse.Namespace(batch=4, frames=80)
+    cfg = bench.workload_config(args, 2)
+    assert cfg['utterances_per_gpu'] == 4 and cfg['global_batch'] == 8 and cfg['steps_per_utterance'] == 80 * 275
+    assert cfg['workload'].startswith('BASELINE config 3')
+    bench._BEST_THREADS = 2                                  # skip the thread probe in the test
+    rate, steps, threads = bench.cpu_oracle_rate(4, max_seconds=0.5)
+    assert rate > 0 and steps >= 10 and threads == 2
+    assert '4 utterances' in bench.cpu_sample_text(4, steps, 80)
