@@ -13,6 +13,19 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'reference: needs /root/reference (build container only)')
 
 
+@pytest.fixture(scope='session', autouse=True)
+def _bounded_blas_pool():
+    """The oracles run thousands of tiny matvecs; more than 4 BLAS threads buys nothing (measured: 61 s with 4, 64 s with 8)
+    and, on a busy or over-committed host, spinning worker threads can stretch the suite from one minute to tens of minutes."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        yield
+        return
+    with threadpool_limits(limits=min(4, os.cpu_count() or 1)):
+        yield
+
+
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 REF_CKPT_COPY = os.path.join(ROOT, 'oracle', '_ref', 'latest_weights.pyt')
 
