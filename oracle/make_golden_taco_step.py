@@ -87,7 +87,7 @@ def main():
     out = {'ids': ids, 'memory': memory, 'steps': np.array(steps)}
     worst = {}
     for s in steps:
-        x, st, m = d['states'][s]
+        x, st, m, _ = d['states'][s]
         g = run_graph_step(nodes, variables, memory, keys, x, m, st)
         o, _ = to.decoder_step(w, memory, keys, x, m, st)
         out[f's{s}_x'], out[f's{s}_m'] = x, m

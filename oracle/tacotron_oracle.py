@@ -11,6 +11,10 @@ projections), the ENCODER (convolution blocks, single BiLSTM iterations, the fw/
 numerically AND structurally against the reference's own serialized graph, executed op by op in numpy on the shipped
 weights.  What has no reference vectors: whole-utterance TensorFlow outputs (the decoder loop iterated, with TF's own
 random masks). ***  Pins that ARE checked:
+  * tests/test_tacotron_window_pins.py: the attention step WITH the optional inference window (row a-9) against the reference's
+    own `ForwardLocationSensitiveAttention.__call__` (forward_attention.py:119-231), whose statements are executed unmodified
+    on numpy arrays through a stand-in for the few tensorflow ops they use (oracle/ref_harness_taco_attention.py ->
+    tests/golden/taco_window_from_reference.npz, 60 loop states covering every branch; measured difference 0.0);
   * tests/test_tacotron_encpost_pins.py: encoder_convs / lstm_cell on the encoder kernels / postnet against the serialized
     sub-graphs (oracle/make_golden_taco_encpost.py -> tests/golden/taco_encpost_from_graph.npz; 2e-7 relative);
   * tests/test_tacotron_step_pins.py: `decoder_step` reproduces (to 1e-6; measured 0.0) every intermediate obtained by
@@ -146,6 +150,33 @@ def location_features(w, cum):
     return (f @ w[P + 'Location_Sensitive_Attention/location_features_layer/kernel']).astype(F32)   # [Tx, 128]
 
 
+def attention_window(al, max_att, pos_rec):
+    """The optional inference window of forward_attention.py:171-215 for one sentence: the attended position may advance
+    by at most one token per step, may not leave token <= 2 before 5 steps have been spent there (`short_mask`), is pushed
+    on after 10 steps on the same token, and the raw forward term `al` [Tx] is zeroed outside [new_max-2, new_max+3) with
+    the entry at new_max set to twice the remaining mass.  Returns (al, new_max, new_pos_rec).
+    tests/test_tacotron_window_pins.py holds this against the reference's own statements executed on numpy arrays."""
+    Tx = al.shape[0]
+    new_max = int(np.argmax(al))
+    new_max = max_att if new_max <= max_att else max_att + 1
+    if pos_rec < 5 and 2 < new_max:
+        new_max = max_att
+    if new_max == max_att:
+        pos_rec = pos_rec + 1
+    else:
+        pos_rec = 1
+    if not pos_rec < 10:                                                                     # :191-195
+        new_max, pos_rec = new_max + 1, 1
+    idx = np.arange(Tx)
+    keep = (idx >= new_max - 2) & (idx < new_max + 3)
+    al = np.where(keep, al, F32(0)).astype(F32)
+    peak = idx == min(max(new_max, 0), Tx - 1)
+    tot = al.sum(dtype=F32)
+    tot = F32(1.0) if tot < F32(1e-10) else tot                                              # :209-213
+    al = np.where(peak & (idx < new_max + 1), tot * F32(2.0), al).astype(F32)                # :215
+    return al, new_max, pos_rec
+
+
 def decoder_step(w, memory, keys, x, m, st, zoneout=GRAPH_ASSUMPTIONS['zoneout'], modulate=None):
     """ONE iteration of the decoder loop: TacotronDecoderCell.__call__ (Architecture_wrappers.py:175-218) with
     Prenet (modules.py:240-251), 2 x ZoneoutLSTMCell (:114-142), ForwardLocationSensitiveAttention.__call__
@@ -208,7 +239,7 @@ def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, 
     memory [Tx, 512]; dropout_masks optional [steps, 2, 256] of {0,1} keep flags for the two prenet layers
     (drawn from RandomState(seed) when None; prenet dropout is ON at inference, modules.py:249).
     Returns dict(frames [n,80] raw decoder outputs, stop [n], alignments [n,Tx], n_steps, masks
-    [, states {step: (x, state)} for the steps listed in `capture_states`]).
+    [, states {step: (x, state, masks, window state)} for the steps listed in `capture_states`]).
     """
     Tx = memory.shape[0]
     keys = (memory @ w['memory_layer/kernel']).astype(F32)                                   # BahdanauAttention ctor
@@ -223,26 +254,8 @@ def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, 
     x = np.zeros((1, 80), dtype=F32)                                                         # _go_frames (helpers.py:149)
     frames, stops, aligns, masks, captured = [], [], [], [], {}
 
-    def window_modulate(al):                                                                 # forward_attention.py:171-215
-        max_att, pos_rec = win['max_att'], win['pos_rec']
-        new_max = int(np.argmax(al))
-        new_max = max_att if new_max <= max_att else max_att + 1
-        if pos_rec < 5 and 2 < new_max:
-            new_max = max_att
-        if new_max == max_att:
-            pos_rec = pos_rec + 1
-        else:
-            pos_rec = 1
-        if not pos_rec < 10:                                                                 # :191-195
-            new_max, pos_rec = new_max + 1, 1
-        idx = np.arange(Tx)
-        keep = (idx >= new_max - 2) & (idx < new_max + 3)
-        al = np.where(keep, al, F32(0)).astype(F32)
-        peak = idx == min(max(new_max, 0), Tx - 1)
-        tot = al.sum(dtype=F32)
-        tot = F32(1.0) if tot < F32(1e-10) else tot                                          # :209-213
-        al = np.where(peak & (idx < new_max + 1), tot * F32(2.0), al).astype(F32)            # :215
-        win['max_att'], win['pos_rec'] = new_max, pos_rec
+    def window_modulate(al):
+        al, win['max_att'], win['pos_rec'] = attention_window(al, win['max_att'], win['pos_rec'])
         return al
 
     for step in range(max_iters):
@@ -250,7 +263,7 @@ def decode(w, memory, dropout_masks=None, seed=0, max_iters=2000, window=False, 
         m = np.asarray(m, dtype=F32)
         masks.append(m)
         if step in capture_states:
-            captured[step] = (x.copy(), {k: np.array(v, copy=True) for k, v in st.items()}, m.copy())
+            captured[step] = (x.copy(), {k: np.array(v, copy=True) for k, v in st.items()}, m.copy(), dict(win))
         out, st = decoder_step(w, memory, keys, x, m, st, zoneout, window_modulate if window else None)
         frame = out['frame']
         stop = _sigmoid(out['stop_logit'])[0, 0]
