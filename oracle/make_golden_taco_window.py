@@ -62,6 +62,13 @@ def main():
     out = {'ids': ids, 'memory': memory}
     for k in rows[0]:
         out[k] = np.stack([np.asarray(r[k]) for r in rows])
+    # the loop driver's stop rule and next input (helpers.py:42-66), from the reference's own TacoTestHelper
+    probs = np.array([0.0, 0.2, 0.49999997, 0.5, 0.50000006, 0.7, 1.0], dtype=np.float32)
+    frame = np.arange(80, dtype=np.float32)[None]
+    res = [R.reference_test_helper_next_inputs(np.array([[p]]), frame) for p in probs]
+    out['helper_stop_probability'] = probs
+    out['helper_finished'] = np.array([r[0] for r in res])
+    assert all(np.array_equal(r[1], frame) for r in res) and not res[0][2].any() and res[0][2].shape == (1, 80)
     path = os.path.join(ROOT, 'tests', 'golden', 'taco_window_from_reference.npz')
     np.savez_compressed(path, **out)
     print(f'wrote {path} ({os.path.getsize(path)} bytes, {len(rows)} steps of {n_run}, run stopped at {d["n_steps"]}); '

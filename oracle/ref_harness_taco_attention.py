@@ -161,3 +161,38 @@ class ReferenceAttention:
         """query [1,256]; state fields batched [1,...].  Returns the reference's 6-tuple."""
         with contextlib.redirect_stdout(io.StringIO()):                                   # the reference prints a banner (:172-174)
             return self.cls.__call__(self.obj, query, state)
+
+
+def reference_test_helper_next_inputs(stop_probabilities, outputs):
+    """Runs the reference's own `TacoTestHelper.next_inputs` (tacotron/models/helpers.py:42-66, hparams of the shipped model:
+    outputs_per_step = 1, stop_at_any = True) on numpy values.  stop_probabilities [B, r], outputs [B, r * num_mels].
+    Returns (finished: bool, next_inputs)."""
+    tf = types.ModuleType('tensorflow')
+    tf.bool = 'bool'
+    tf.name_scope = lambda *a, **k: contextlib.nullcontext()
+    tf.round = lambda x: np.round(x)                                  # half-to-even, like tf.round
+    tf.cast = lambda x, dt: np.asarray(x).astype(np.bool_ if dt == 'bool' else dt)
+    tf.reduce_all = lambda x, axis=None: np.all(x, axis=axis)
+    tf.reduce_any = lambda x, axis=None: np.any(x, axis=axis)
+    tf.tile = lambda x, m: np.tile(np.asarray(x), m)
+    tf.TensorShape = lambda x: tuple(x)
+    seq2seq = types.ModuleType('tensorflow.contrib.seq2seq')
+    seq2seq.Helper = type('Helper', (), {})
+    fake = {'tensorflow': tf, 'tensorflow.contrib': types.ModuleType('tensorflow.contrib'), 'tensorflow.contrib.seq2seq': seq2seq}
+    saved = {k: sys.modules.get(k) for k in fake}
+    sys.modules.update(fake)
+    try:
+        spec = importlib.util.spec_from_file_location('_ref_helpers', os.path.join(REF_ROOT, 'tacotron/models/helpers.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    hp = types.SimpleNamespace(outputs_per_step=1, use_all_outputs=False, num_mels=80, stop_at_any=True)
+    helper = mod.TacoTestHelper(batch_size=np.shape(outputs)[0], hparams=hp, input_seq_lengths=None)
+    _, go = helper.initialize()
+    finished, nxt, _ = helper.next_inputs(0, np.asarray(outputs), None, None, np.asarray(stop_probabilities, dtype=np.float32))
+    return bool(finished), np.asarray(nxt), np.asarray(go)

@@ -61,3 +61,11 @@ def test_windowed_attention_step_matches_reference_statements(ctx):
         np.testing.assert_allclose((cum + a).astype(np.float32), z['ref_cum'][i], rtol=0, atol=1e-6)
         np.testing.assert_allclose(ctxv[0], z['ref_context'][i], rtol=0, atol=1e-5)
         assert abs(float(new_mu) - float(z['ref_mu'][i])) <= 1e-6
+
+
+def test_stop_rule_matches_reference_helper(ctx):
+    """decode() stops when `stop > 0.5`: that is tf.round (half-to-even) == 1 in the reference's TacoTestHelper.next_inputs."""
+    _, z = ctx
+    ours = z['helper_stop_probability'] > 0.5
+    np.testing.assert_array_equal(ours, z['helper_finished'])
+    assert not ours[3] and ours[4]                                  # exactly 0.5 does not stop; the next float above does
