@@ -69,6 +69,15 @@ def main():
     out['helper_stop_probability'] = probs
     out['helper_finished'] = np.array([r[0] for r in res])
     assert all(np.array_equal(r[1], frame) for r in res) and not res[0][2].any() and res[0][2].shape == (1, 80)
+    # zoneout at inference (modules.py:137-138) and the cell output, from the reference's own ZoneoutLSTMCell
+    rs = np.random.RandomState(5)
+    k1 = w['decoder/decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/kernel']
+    b1 = w['decoder/decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/bias']
+    zx, zc, zh = (rs.randn(1, n).astype(np.float32) for n in (768, 256, 256))
+    zo = R.reference_zoneout_lstm(zx, zc, zh, k1, b1, to.lstm_cell)
+    out.update(zoneout_x=zx, zoneout_c=zc, zoneout_h=zh, zoneout_ref_output=zo[0], zoneout_ref_c=zo[1], zoneout_ref_h=zo[2])
+    mine = to.zoneout_lstm(zx, zc, zh, k1, b1)
+    print('zoneout cell: oracle vs reference statements', [float(np.abs(a - b).max()) for a, b in zip(mine, zo)])
     path = os.path.join(ROOT, 'tests', 'golden', 'taco_window_from_reference.npz')
     np.savez_compressed(path, **out)
     print(f'wrote {path} ({os.path.getsize(path)} bytes, {len(rows)} steps of {n_run}, run stopped at {d["n_steps"]}); '

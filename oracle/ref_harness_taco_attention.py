@@ -196,3 +196,39 @@ def reference_test_helper_next_inputs(stop_probabilities, outputs):
     _, go = helper.initialize()
     finished, nxt, _ = helper.next_inputs(0, np.asarray(outputs), None, None, np.asarray(stop_probabilities, dtype=np.float32))
     return bool(finished), np.asarray(nxt), np.asarray(go)
+
+
+def reference_zoneout_lstm(x, c, h, kernel, bias, lstm_cell, zoneout=0.1):
+    """Runs the reference's own `ZoneoutLSTMCell` (tacotron/models/modules.py:81-142; real constructor, real `__call__`,
+    is_training = False) with the inner `tf.nn.rnn_cell.LSTMCell` replaced by `lstm_cell(x, c, h, kernel, bias) ->
+    (new_c, new_h)` (that arithmetic is pinned separately against the serialized graph).  What this executes is the
+    reference's zoneout statement at inference and which h it returns as the cell OUTPUT.  Returns (output, c, h)."""
+    StateTuple = collections.namedtuple('LSTMStateTuple', 'c h')
+
+    class LSTMCell:
+        def __init__(self, num_units, state_is_tuple=True, name=None):
+            self._num_units, self._num_proj = num_units, None
+
+        def __call__(self, inputs, state, scope=None):
+            new_c, new_h = lstm_cell(inputs, state[0], state[1], kernel, bias)
+            return new_h, StateTuple(new_c, new_h)                    # tf LSTMCell: output = new_h, state = (new_c, new_h)
+
+    tf = types.ModuleType('tensorflow')
+    tf.nn = types.SimpleNamespace(rnn_cell=types.SimpleNamespace(RNNCell=object, LSTMCell=LSTMCell, LSTMStateTuple=StateTuple),
+                                  relu=None, sigmoid=None, tanh=None)
+    tf.layers = types.SimpleNamespace(Dense=lambda *a, **k: None)
+    tf.constant_initializer = lambda *a, **k: None
+    saved = sys.modules.get('tensorflow')
+    sys.modules['tensorflow'] = tf
+    try:
+        spec = importlib.util.spec_from_file_location('_ref_modules', os.path.join(REF_ROOT, 'tacotron/models/modules.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is None:
+            sys.modules.pop('tensorflow', None)
+        else:
+            sys.modules['tensorflow'] = saved
+    cell = mod.ZoneoutLSTMCell(kernel.shape[1] // 4, is_training=False, zoneout_factor_cell=zoneout, zoneout_factor_output=zoneout)
+    out, new_state = cell(x, StateTuple(c, h))
+    return np.asarray(out), np.asarray(new_state.c), np.asarray(new_state.h)

@@ -14,7 +14,8 @@ random masks). ***  Pins that ARE checked:
   * tests/test_tacotron_window_pins.py: the attention step WITH the optional inference window (row a-9) against the reference's
     own `ForwardLocationSensitiveAttention.__call__` (forward_attention.py:119-231), whose statements are executed unmodified
     on numpy arrays through a stand-in for the few tensorflow ops they use (oracle/ref_harness_taco_attention.py ->
-    tests/golden/taco_window_from_reference.npz, 60 loop states covering every branch; measured difference 0.0);
+    tests/golden/taco_window_from_reference.npz, 60 loop states covering every branch; measured difference 0.0); the same
+    file pins the stop rule (the reference's TacoTestHelper) and zoneout at inference (its ZoneoutLSTMCell class);
   * tests/test_tacotron_encpost_pins.py: encoder_convs / lstm_cell on the encoder kernels / postnet against the serialized
     sub-graphs (oracle/make_golden_taco_encpost.py -> tests/golden/taco_encpost_from_graph.npz; 2e-7 relative);
   * tests/test_tacotron_step_pins.py: `decoder_step` reproduces (to 1e-6; measured 0.0) every intermediate obtained by

@@ -69,3 +69,16 @@ def test_stop_rule_matches_reference_helper(ctx):
     ours = z['helper_stop_probability'] > 0.5
     np.testing.assert_array_equal(ours, z['helper_finished'])
     assert not ours[3] and ours[4]                                  # exactly 0.5 does not stop; the next float above does
+
+
+def test_zoneout_cell_matches_reference_class(ctx):
+    """ZoneoutLSTMCell at inference (modules.py:114-142, the reference's real class around a stand-in LSTMCell): the cell
+    OUTPUT is the un-zoned h, the carried state is 0.9 * new + 0.1 * prev."""
+    w, z = ctx
+    k1 = w['decoder/decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/kernel']
+    b1 = w['decoder/decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/bias']
+    out, c, h = to.zoneout_lstm(z['zoneout_x'], z['zoneout_c'], z['zoneout_h'], k1, b1)
+    np.testing.assert_allclose(out, z['zoneout_ref_output'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(c, z['zoneout_ref_c'], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(h, z['zoneout_ref_h'], rtol=1e-6, atol=1e-6)
+    assert np.abs(out - h).max() > 1e-3                              # output and carried h really differ
