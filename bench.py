@@ -4,15 +4,19 @@
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...       # the reference algorithm on the host cores (oracle port)
+    python bench.py --impl reference ...       # the UNMODIFIED reference's generate() on the host cores
 
-One "step" = one full pass of the hot path (conditioning network + all T*hop autoregressive sample steps +
-mu-law decode/fade) over this rank's batch of synthetic 80-frame mels.  Workload = BASELINE config 3
-(batch=256 utterances of 80 frames); per-GPU work is fixed as N grows ("weak"), utterances are sharded with no
-data-path collective, and for N > 1 every timed step ends with the NCCL all-gather of the int16 labels.
+One "step" = one full pass of the hot path (conditioning network + all T*hop autoregressive sample steps + mu-law
+decode/fade) over this rank's batch of synthetic 80-frame mels, on the SHIPPED checkpoint when its travel copy is present
+(oracle/_ref/latest_weights.pyt, made by __graft_entry__.build()), else on random-init weights of the same architecture.
 
-Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the C-ABI host
-entry point (b200tts_wavernn_generate_host: pinned H2D of the mels, generation, D2H of labels + float64 wave).
+Headline line (`value`, `scaling: weak`): BASELINE config 3 with 256 utterances PER GPU -- utterances are sharded with no
+data-path collective and for N > 1 every timed step ends with the NCCL all-gather of the int16 labels.  BASELINE config 3 AS
+WRITTEN is a 256-utterance GLOBAL batch over 8 GPUs: that is the `strong` object of the same JSON line (256/N per GPU,
+measured in the same run with the same timing rules).
+
+Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the C-ABI host entry
+point (b200tts_wavernn_generate_host: pinned H2D of the mels, generation, D2H of labels + float64 wave).
 """
 from __future__ import annotations
 
@@ -32,6 +36,8 @@ HOP, FEAT, NCLS = 275, 80, 1024
 STEP_WEIGHT_BYTES = 17_371_136          # all per-step weights + biases, fp32, touched once per lock-step
 COND_BYTES_PER_UTT = 836                # 80 mel + 128 aux fp32 in, 4 B out, per utterance-sample
 FLOP_PER_SAMPLE = 8_668_160             # 2 * 4 334 080 MAC per utterance-sample
+CKPT_TRAVEL = os.path.join(ROOT, 'oracle', '_ref', 'latest_weights.pyt')
+CKPT_CONTAINER = '/root/reference/logs_wavernn/checkpoints/latest_weights.pyt'
 
 
 def parse():
@@ -40,9 +46,11 @@ def parse():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', choices=('b200', 'reference'), default='b200')
-    ap.add_argument('--batch', type=int, default=256, help='utterances per GPU')
+    ap.add_argument('--batch', type=int, default=256, help='utterances per GPU (weak line) = global batch of the strong line')
     ap.add_argument('--frames', type=int, default=80)
     ap.add_argument('--kernel', default='auto', choices=('auto', 'grid', 'utterance'))
+    ap.add_argument('--weights', default='auto', choices=('auto', 'shipped', 'synthetic'))
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling (global batch) measurement')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -93,121 +101,207 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
 
 
-_BEST_THREADS = None
+# ------------------------------------------------------------------------------------------------
+# weights: the drop-in checkpoint when it is on the box
+# ------------------------------------------------------------------------------------------------
+def load_weights(which):
+    from tacotronv2_wavernn_chinese_b200 import synth
+    if which in ('auto', 'shipped'):
+        for p in (CKPT_TRAVEL, CKPT_CONTAINER):
+            if os.path.isfile(p):
+                import torch
+                sd = torch.load(p, map_location='cpu', weights_only=True)
+                return {k: v.numpy() for k, v in sd.items()}, 'shipped checkpoint latest_weights.pyt (step 617k)'
+        if which == 'shipped':
+            raise SystemExit('--weights shipped: no travel copy of the checkpoint (run __graft_entry__.build() in the container)')
+    return synth.synth_state_dict(0), 'random-init weights of the shipped architecture (synth.synth_state_dict(0))'
 
 
-_CPU_CACHE = {}
+# ------------------------------------------------------------------------------------------------
+# CPU arms.  kind "_ref": the UNMODIFIED reference WaveRNN.generate (fatchord_version.py:169), imported from the git-ignored
+# travel copy oracle/_ref/reference_src.zip through oracle/ref_harness.py, shipped checkpoint, torch CPU.
+# kind "port": the numpy oracle port (oracle/wavernn_oracle.py), kept beside it for continuity with round 1.
+# ------------------------------------------------------------------------------------------------
+_REF = {}
 
 
-def _cpu_workload(batch):
-    """Weights + conditioning of the CPU arm, built once per process: `batch` utterances (the arm's own batch size, so the
-    host runs [batch x K] GEMMs like the reference's loop would on a [batch, 80, T] mel), minimum-length mels (21 frames:
-    the per-step cost does not depend on the utterance length), 8 distinct utterances tiled to `batch` rows (it does not
-    depend on the values either; the numpy conditioning network would otherwise take ~0.3 s per utterance)."""
-    if batch not in _CPU_CACHE:
-        from oracle import wavernn_oracle as wo
-        from tacotronv2_wavernn_chinese_b200 import synth
-        p = {k: (v.astype(np.float32) if v.dtype.kind == 'f' else v) for k, v in wo.as_params(synth.synth_state_dict(0)).items()}
-        distinct = min(8, batch)
-        mels = synth.synth_mels(1234, distinct, 21)
-        d = wo._dims(p)
-        mp = wo.pad_tensor(mels.transpose(0, 2, 1), d['pad'], 'both').transpose(0, 2, 1)
-        m_up, aux = wo.upsample(p, mp)
-        reps = (batch + distinct - 1) // distinct
-        tile = lambda a: np.ascontiguousarray(np.tile(a, (reps, 1, 1))[:batch])
-        _CPU_CACHE[batch] = (wo, p, tile(mels), (tile(m_up), tile(aux)))
-    return _CPU_CACHE[batch]
+def ref_model():
+    if 'model' not in _REF:
+        from oracle import ref_harness as rh
+        if not rh.available():
+            _REF['model'] = None
+        else:
+            m = rh.build_model()
+            rh.memoize_upsample(m)
+            _REF['model'], _REF['rh'] = m, rh
+    return _REF['model']
 
 
-def _pick_threads(batch):
-    """Probe a few BLAS pool sizes on the actual workload and keep the fastest -- "all the host threads it can USE"
-    (at batch 1 the matvecs are tiny and more than ~16 threads only adds contention; at batch 256 the GEMMs scale further)."""
-    global _BEST_THREADS
-    if _BEST_THREADS is not None:
-        return _BEST_THREADS
+def ref_pick_threads(batch, mels):
+    """"All the host threads it can USE": probe a few torch intra-op pool sizes on the actual batch, keep the fastest."""
+    import torch
+    key = ('threads', batch)
+    if key in _REF:
+        return _REF[key]
+    rh, m = _REF['rh'], _REF['model']
     ncpu = os.cpu_count() or 1
-    try:
-        from threadpoolctl import threadpool_limits
-    except Exception:
-        _BEST_THREADS = ncpu
-        return ncpu
-    wo, p, mels, cond = _cpu_workload(batch)
-    n = 30 if batch > 1 else 150
     best, best_rate = 1, 0.0
-    for nt in sorted({1, 4, 8, 16, 32, 64, ncpu} & set(range(1, ncpu + 1))):
-        with threadpool_limits(limits=nt):
-            wo.generate(p, mels, max_steps=3, seed=0, cond=cond)
-            r = wo.generate(p, mels, max_steps=n, seed=0, cond=cond)
-        rate = n / r['loop_seconds']
+    rh.timed_generate_sample(m, mels, max_steps=4)                         # conditioning network once (memoised afterwards)
+    for nt in sorted({1, 8, 16, 32, 64, ncpu} & set(range(1, ncpu + 1))):
+        torch.set_num_threads(nt)
+        r = rh.timed_generate_sample(m, mels, max_seconds=1.0 if batch > 1 else 0.5)
+        rate = r['steps'] / r['loop_seconds']
         if rate > best_rate:
             best, best_rate = nt, rate
-    _BEST_THREADS = best
+    torch.set_num_threads(best)
+    _REF[key] = best
     return best
 
 
-def cpu_oracle_rate(batch, max_seconds=25.0):
-    """The reference algorithm (numpy oracle port, oracle/wavernn_oracle.py) on the host cores, on the arm's batch size:
-    as many lock-steps of `batch` utterances as fit the time bound; the one-shot conditioning network is outside the timed
-    loop (see _cpu_workload).  Returns (samples/s, lock-steps run, threads used)."""
+def ref_sample(batch, max_seconds):
+    """One bounded sample of the reference's own sampling loop on `batch` utterances -> dict(value samples/s, steps, threads)."""
+    import torch
+    from tacotronv2_wavernn_chinese_b200 import synth
+    m = ref_model()
+    rh = _REF['rh']
+    key = ('mels', batch)
+    if key not in _REF:
+        _REF[key] = torch.as_tensor(synth.synth_mels(1236, batch, 21))     # minimum length: per-step cost is length-independent
+    mels = _REF[key]
+    threads = ref_pick_threads(batch, mels)
+    torch.set_num_threads(threads)
+    r = rh.timed_generate_sample(m, mels, max_seconds=max_seconds)
+    return dict(value=batch * r['steps'] / r['loop_seconds'], steps=r['steps'], threads=threads, seconds=r['loop_seconds'])
+
+
+def ref_config1():
+    """BASELINE config 1: what the reference's CLI does -- ONE 80-frame utterance, all 22 000 steps, conditioning included."""
+    import torch
+    from tacotronv2_wavernn_chinese_b200 import synth
+    m = ref_model()
+    rh = _REF['rh']
+    mel = torch.as_tensor(synth.synth_mels(1234, 1, 80))
+    threads = ref_pick_threads(1, torch.as_tensor(synth.synth_mels(1234, 1, 21)))
+    torch.set_num_threads(threads)
+    m.upsample._b200_memo.clear()
+    t0 = time.perf_counter()
+    r = rh.timed_generate_sample(m, mel)
+    wall = time.perf_counter() - t0
+    S = 80 * HOP
+    return dict(samples_per_s=S / wall, rtf=wall / ((79 * HOP) / 22050.0), seconds=wall, loop_seconds=r['loop_seconds'],
+                conditioning_seconds=r['upsample_seconds'], steps=r['steps'], threads=threads,
+                what='unmodified reference WaveRNN.generate(mel[1,80,80], batched=False), shipped checkpoint, torch CPU')
+
+
+_PORT = {}
+
+
+def port_sample(batch, max_seconds):
+    """The numpy oracle port on the same batch (sampling loop only), BLAS threads chosen by probe."""
     import contextlib
-    wo, p, mels, cond = _cpu_workload(batch)
-    threads = _pick_threads(batch)
+    from oracle import wavernn_oracle as wo
+    from tacotronv2_wavernn_chinese_b200 import synth
+    if batch not in _PORT:
+        p = {k: (v.astype(np.float32) if v.dtype.kind == 'f' else v) for k, v in wo.as_params(synth.synth_state_dict(0)).items()}
+        distinct = min(8, batch)
+        mels = synth.synth_mels(1234, distinct, 21)
+        mp = wo.pad_tensor(mels.transpose(0, 2, 1), wo._dims(p)['pad'], 'both').transpose(0, 2, 1)
+        m_up, aux = wo.upsample(p, mp)
+        reps = (batch + distinct - 1) // distinct
+        tile = lambda a: np.ascontiguousarray(np.tile(a, (reps, 1, 1))[:batch])
+        _PORT[batch] = (wo, p, tile(mels), (tile(m_up), tile(aux)))
+    wo, p, mels, cond = _PORT[batch]
     try:
         from threadpoolctl import threadpool_limits
-        ctx = threadpool_limits(limits=threads)
     except Exception:
-        ctx = contextlib.nullcontext()
+        threadpool_limits = None
+    ncpu = os.cpu_count() or 1
+    if ('t', batch) not in _PORT:
+        best, best_rate = ncpu, 0.0
+        if threadpool_limits is not None:
+            for nt in sorted({1, 8, 16, 32, ncpu} & set(range(1, ncpu + 1))):
+                with threadpool_limits(limits=nt):
+                    wo.generate(p, mels, max_steps=3, seed=0, cond=cond)
+                    r = wo.generate(p, mels, max_steps=20 if batch > 1 else 100, seed=0, cond=cond)
+                rate = r['steps'] / r['loop_seconds']
+                if rate > best_rate:
+                    best, best_rate = nt, rate
+        _PORT[('t', batch)] = best
+    threads = _PORT[('t', batch)]
+    ctx = threadpool_limits(limits=threads) if threadpool_limits is not None else contextlib.nullcontext()
     with ctx:
         probe = wo.generate(p, mels, max_steps=10, seed=0, cond=cond)
         per_step = max(probe['loop_seconds'] / 10, 1e-6)
         steps = int(min(mels.shape[2] * HOP, max(10, max_seconds / per_step)))
         r = wo.generate(p, mels, max_steps=steps, seed=0, cond=cond)
-    return batch * steps / r['loop_seconds'], steps, threads
+    return dict(value=batch * steps / r['loop_seconds'], steps=steps, threads=threads)
 
 
-def workload_config(args, N):
-    """The `config` object both arms print (BASELINE config 3)."""
+def cpu_baseline(batch, frames, seconds):
+    """cpu_baseline object of the b200 line / the reference arm: `_ref` when the travel copy is there, the port otherwise."""
+    if ref_model() is not None:
+        r = ref_sample(batch, seconds)
+        out = {'value': r['value'], 'unit': 'samples/s', 'cores': r['threads'], 'kind': '_ref',
+               'sample': f"{batch} utterances x {r['steps']} of {frames * HOP} lock-steps of the UNMODIFIED reference "
+                         f"WaveRNN.generate loop (fatchord_version.py:201-241, shipped checkpoint, torch CPU, {r['threads']} intra-op "
+                         f"threads picked by probe on a {os.cpu_count()}-thread host); the one-shot conditioning network is "
+                         f"outside the timed region (21-frame mels: the per-step cost does not depend on the length)"}
+        try:
+            pr = port_sample(batch, min(seconds, 6.0))
+            out['port'] = {'value': pr['value'], 'cores': pr['threads'], 'kind': 'port',
+                           'sample': f"{batch} utterances x {pr['steps']} lock-steps, numpy oracle port, random-init weights"}
+        except Exception as e:                                               # the port is a side note, never fatal
+            out['port'] = {'error': str(e)[:200]}
+        return out
+    pr = port_sample(batch, seconds)
+    return {'value': pr['value'], 'unit': 'samples/s', 'cores': pr['threads'], 'kind': 'port',
+            'sample': f"{batch} utterances x {pr['steps']} of {frames * HOP} lock-steps, numpy oracle port of generate() "
+                      f"(the reference's travel copy oracle/_ref/reference_src.zip is absent: run __graft_entry__.build() in the container)"}
+
+
+def workload_config(args, N, wdesc):
     B, T = args.batch, args.frames
-    return {'workload': f'BASELINE config 3: WaveRNN generate(), batch={B} utterances/GPU of {T}-frame synthetic '
-                        f'mels (voc_mode=RAW bits=10 hop=275), random-init weights of the shipped architecture',
+    return {'workload': f'BASELINE config 3: WaveRNN generate(), batch={B} utterances/GPU of {T}-frame synthetic mels '
+                        f'(voc_mode=RAW bits=10 hop=275), {wdesc}',
             'utterances_per_gpu': B, 'global_batch': N * B, 'frames': T, 'steps_per_utterance': T * HOP}
 
 
-def cpu_sample_text(batch, steps_run, frames):
-    return (f'{batch} utterances x {steps_run} of {frames * HOP} lock-steps per bench step, sampling loop only (the one-shot '
-            f'conditioning network is outside the timed region); numpy oracle port of generate(), fp32, BLAS threads chosen by probe')
-
-
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the host cores, on the b200 arm's workload (the Python reference itself
-    cannot travel to the GPU box; this is the oracle port, pinned bit-for-bit to the reference's labels by
-    tests/test_oracle_golden.py).  Each bench step is a time-bounded sample of the 22 000 lock-steps of the batch."""
+    """--impl reference: the reference's own generate() loop on the host cores, on the b200 arm's batch.  Each bench step
+    is a time-bounded sample of the 22 000 lock-steps of the 256-utterance batch; BASELINE config 1 (what the reference's
+    CLI does: one utterance, all steps) is measured once and reported beside it."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    per_step_budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
-    rates, steps_run, threads = [], 0, 1
+    have_ref = ref_model() is not None
+    per_step_budget = max(1.5, min(8.0, 110.0 / max(1, args.steps + args.warmup)))
+    rates, last = [], None
     for i in range(args.warmup + args.steps):
-        rate, steps_run, threads = cpu_oracle_rate(args.batch, max_seconds=per_step_budget)
+        last = ref_sample(args.batch, per_step_budget) if have_ref else port_sample(args.batch, per_step_budget)
         if i >= args.warmup:
-            rates.append(rate)
+            rates.append(last['value'])
     v = float(np.mean(rates))
-    cfg = workload_config(args, 1)
-    cfg['parallelism'] = f'host CPU, {threads} BLAS threads (rank 0 only)'
+    cfg = workload_config(args, 1, 'shipped checkpoint' if have_ref else 'random-init weights')
+    cfg['parallelism'] = f"host CPU, {last['threads']} threads (rank 0 only)"
+    base = cpu_baseline(args.batch, args.frames, 4.0)
+    base['value'] = v
     line = {
         'impl': 'reference', 'metric': 'wavernn_audio_samples_per_sec', 'value': v, 'unit': 'samples/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * args.batch * steps_run / v,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * args.batch * last['steps'] / last['value'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': cfg,
-        'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-                         'sample': cpu_sample_text(args.batch, steps_run, args.frames)},
+        'config': cfg, 'cpu_baseline': base,
         'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
-        'rtf': 22050.0 / (v / args.batch),
+        'gpu_launches': 0, 'rtf': 22050.0 / (v / args.batch), 'host_threads': os.cpu_count(),
     }
+    if have_ref:
+        try:
+            line['config1_reference_cli'] = ref_config1()
+        except Exception as e:
+            line['config1_reference_cli'] = {'error': str(e)[:200]}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -231,12 +325,9 @@ def main():
     B, T = args.batch, args.frames
     S, wave_len = T * HOP, (T - 1) * HOP
 
-    eng = WaveRNNEngine(synth.synth_state_dict(0), synth.DEFAULT_DIMS, device=local)
-    mels_host = synth.synth_mels(1236 + rank, B, T)                       # this rank's shard of the global batch
-    mels_dev = torch.as_tensor(mels_host).to(dev)
+    sd, wdesc = load_weights(args.weights)
+    eng = WaveRNNEngine(sd, synth.DEFAULT_DIMS, device=local)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)   # > 126 MB L2
-    # NCCL has no int16: the labels travel as raw bytes
-    gathered = [torch.empty(B, S * 2, device=dev, dtype=torch.uint8) for _ in range(N)] if N > 1 else None
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -244,45 +335,64 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def one_step(i):
-        flush.fill_(float(i))                                              # evict L2 between iterations
-        out = eng.generate(mels_dev, seed=20260923, utterance_offset=rank * B, kernel=args.kernel)
-        if N > 1:
-            dist.all_gather(gathered, out['labels'].view(torch.uint8))
-        return out
+    def measure(per_gpu, global_offset, steps, warmup):
+        """Times `steps` passes over this rank's `per_gpu` utterances (rows global_offset ... of the global batch)."""
+        mels_dev = torch.as_tensor(synth.synth_mels(1236 + global_offset, per_gpu, T)).to(dev)
+        # NCCL has no int16: the labels travel as raw bytes
+        gathered = [torch.empty(per_gpu, S * 2, device=dev, dtype=torch.uint8) for _ in range(N)] if N > 1 else None
 
-    for i in range(args.warmup):
-        one_step(i)
-    sync_all()
+        def one_step(i):
+            flush.fill_(float(i))                                          # evict L2 between iterations
+            out = eng.generate(mels_dev, seed=20260923, utterance_offset=global_offset, kernel=args.kernel)
+            if N > 1:
+                dist.all_gather(gathered, out['labels'].view(torch.uint8))
+            return out
+
+        for i in range(warmup):
+            one_step(i)
+        sync_all()
+        launches0 = eng.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            one_step(i)
+        ev1.record()
+        sync_all()
+        eng.check()
+        ms = ev0.elapsed_time(ev1)
+        launches = eng.launch_count - launches0 + steps           # + the L2 flush fill per step
+        kms = []
+        for i in range(min(3, max(1, steps))):                    # the dominant kernel's own duration (events inside the library)
+            one_step(i)
+            kms.append(eng.last_kernel_ms())
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if N > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), float(np.mean(kms)), int(launches)
+
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    ev0.record()
-    for i in range(args.steps):
-        one_step(i)
-        kernel_ms.append(None)
-    ev1.record()
-    sync_all()
-    ms = ev0.elapsed_time(ev1)
+    ms, gen_ms, launches = measure(B, rank * B, args.steps, args.warmup)
     clocks = sampler.stop()
-    launches = eng.launch_count - launches0 + args.steps          # + the L2 flush fill per step
-    # the dominant kernel's own duration (CUDA events recorded around it on the launch stream by the library)
-    kms = []
-    for i in range(min(3, max(1, args.steps))):
-        one_step(i)
-        kms.append(eng.last_kernel_ms())
-    gen_ms = float(np.mean(kms))
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if N > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     value = N * B * S * args.steps / (ms / 1e3)
+
+    # ---- BASELINE config 3 as written: the SAME 256 utterances as a global batch, 256/N per GPU ("strong") ----------
+    strong = None
+    if not args.no_strong:
+        if N == 1:
+            strong = {'global_batch': B, 'utterances_per_gpu': B, 'value': value, 'ms_per_step': ms / args.steps,
+                      'us_per_lockstep': 1e3 * gen_ms / S, 'note': 'N = 1: identical to the weak line'}
+        elif B % N == 0:
+            per = B // N
+            sms, sgen, _ = measure(per, rank * per, args.steps, max(3, args.warmup))
+            strong = {'global_batch': B, 'utterances_per_gpu': per, 'value': B * S * args.steps / (sms / 1e3), 'unit': 'samples/s',
+                      'ms_per_step': sms / args.steps, 'us_per_lockstep': 1e3 * sgen / S,
+                      'note': 'BASELINE config 3 as written (256 utterances sharded over the GPUs); efficiency = value / (N x the N=1 value)'}
 
     # ---- end to end through the C-ABI host entry point --------------------------------------------------
     e2e = None
     if not args.no_e2e:
+        mels_host = synth.synth_mels(1236 + rank * B, B, T)
         eng.generate_host(mels_host, seed=1)                                # warm the pinned staging buffers
         sync_all()
         t0 = time.perf_counter()
@@ -293,7 +403,7 @@ def main():
         if N > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        assert res['wave'].shape == (B, wave_len)
+        assert res['wave'].shape == (B, wave_len) and np.isfinite(res['wave'][:, :8]).all()
         e2e = {'value': N * B * S * args.steps / dt, 'unit': 'samples/s',
                'h2d_bytes_per_step': int(N * B * FEAT * T * 4),
                'd2h_bytes_per_step': int(N * B * (S * 2 + wave_len * 8))}
@@ -309,36 +419,44 @@ def main():
         alg_bytes = S * (STEP_WEIGHT_BYTES + B * COND_BYTES_PER_UTT)       # per launch of the generation kernel
         achieved = alg_bytes / (gen_ms / 1e3) / 1e9
         sm_mhz = clocks.get('sm_mhz') or 1965.0
-        fp32_peak_tflops = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-        flops = B * S * FLOP_PER_SAMPLE / (gen_ms / 1e3) / 1e12
-        traffic = None
+        nominal_fp32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('dram_bytes_per_launch')
+            fp32_measured = eng.fp32_peak_tflops()
+        except Exception:
+            fp32_measured = None
+        flops = B * S * FLOP_PER_SAMPLE / (gen_ms / 1e3) / 1e12
+        traffic, traffic_note = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+            traffic, traffic_note = tj.get('dram_bytes_per_launch'), tj.get('captured_on')
         except Exception:
             pass
+        fpeak = fp32_measured or nominal_fp32
         line = {
             'metric': 'wavernn_audio_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': N,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': dict(workload_config(args, N), kernel=args.kernel, l2='flushed between timed iterations (256 MiB fill)',
+            'config': dict(workload_config(args, N, wdesc), kernel=args.kernel, l2='flushed between timed iterations (256 MiB fill)',
                            parallelism=f'utterance-sharded x{N}, NCCL all-gather of labels' if N > 1 else 'single GPU'),
             'rtf': 22050.0 / (value / (N * B)),
             'us_per_lockstep': 1e3 * gen_ms / S,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                         'traffic': traffic, 'peak_source': peak_src,
+                         'traffic': traffic, 'traffic_captured_on': traffic_note, 'peak_source': peak_src,
                          'note': 'weights are SMEM-stationary, so the HBM form is small by construction; the binding '
-                                 'resource is fp32 FMA issue (see flop_form)',
+                                 'resources are fp32 FMA issue and the L2->SM broadcast of the activations (see flop_form)',
                          'kernel_ms': gen_ms, 'algorithmic_bytes_per_launch': alg_bytes,
-                         'flop_form': {'achieved': flops, 'peak': fp32_peak_tflops, 'unit': 'TFLOP/s fp32 CUDA-core',
-                                       'frac': flops / fp32_peak_tflops}},
+                         'flop_form': {'achieved': flops, 'peak': fpeak, 'unit': 'TFLOP/s fp32 CUDA-core',
+                                       'frac': flops / fpeak,
+                                       'peak_source': 'measured: register-only FFMA2 loop on all SMs (b200tts_debug_fp32_peak)'
+                                       if fp32_measured else 'nominal 148 SM x 128 FMA/clk x 2 x SM clock',
+                                       'nominal_peak': nominal_fp32, 'frac_of_nominal': flops / nominal_fp32}},
             'clocks': clocks,
             'gpu_launches': int(launches),
             'e2e': e2e,
+            'strong': strong,
         }
         if not args.no_cpu_baseline and N == 1:        # reported baseline: rank 0, single-GPU runs only
-            rate, steps_run, threads = cpu_oracle_rate(B, max_seconds=15.0)
-            line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-                                    'sample': cpu_sample_text(B, steps_run, T)}
+            line['cpu_baseline'] = cpu_baseline(B, T, 12.0)
         print(json.dumps(line), flush=True)
     if N > 1:
         dist.barrier()

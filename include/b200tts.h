@@ -144,6 +144,16 @@ int64_t b200tts_wavernn_launch_count(const b200tts_wavernn* ctx);
  * generate call; blocks until that kernel has finished.  Negative on error. */
 double b200tts_wavernn_last_kernel_ms(b200tts_wavernn* ctx);
 
+/* Synchronises the device and reports whether the most recent generate call on this context completed: the persistent
+ * generation kernels spin on data written by peer thread blocks and give up after ~2 s (B200TTS_ECUDA, the wave of that call
+ * is filled with NaN).  The stream-ordered b200tts_wavernn_generate cannot report this itself; callers that hand audio to a
+ * user (WaveRNN.generate <- fatchord_version.py:169, wavernn_gen.py:41) call this after their own synchronisation point. */
+int b200tts_wavernn_check(b200tts_wavernn* ctx);
+
+/* Measured fp32 CUDA-core ceiling of `device` in TFLOP/s (register-only packed FFMA2 loop on every SM): the denominator
+ * of bench.py's FLOP-form roofline. */
+int b200tts_debug_fp32_peak(int device, double* tflops);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Tacotron-2 forward-attention decoder loop (secondary hot path).
  *   b200tts_taco_create  <- the decoder-side variables tf.train.Saver restores (tacotron_synthesize.py:76-78), by their

@@ -17,8 +17,43 @@ import contextlib
 import numpy as np
 import torch
 
-REF_ROOT = os.environ.get('B200TTS_REFERENCE', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference exists only in the build container.  __graft_entry__.build() makes a git-ignored TRAVEL COPY of the
+# reference's own `wavernn/` package + `wavernn_hparams.py` + checkpoint under oracle/_ref/ (never committed) so that
+# bench.py's CPU arm can run the UNMODIFIED reference on the GPU box's host cores.
+TRAVEL_ZIP = os.path.join(_HERE, '_ref', 'reference_src.zip')
+TRAVEL_CKPT = os.path.join(_HERE, '_ref', 'latest_weights.pyt')
+_unpacked = None
+
+
+def _travel_root():
+    """Unpacks the travel archive into a fresh temp dir (removed at interpreter exit) and returns it, or None."""
+    global _unpacked
+    if _unpacked is None and os.path.isfile(TRAVEL_ZIP):
+        import atexit
+        import shutil
+        import tempfile
+        import zipfile
+        d = tempfile.mkdtemp(prefix='b200tts_ref_')
+        with zipfile.ZipFile(TRAVEL_ZIP) as z:
+            z.extractall(d)
+        atexit.register(shutil.rmtree, d, True)
+        _unpacked = d
+    return _unpacked
+
+
+def _pick_root():
+    env = os.environ.get('B200TTS_REFERENCE')
+    for cand in (env, '/root/reference'):
+        if cand and os.path.isfile(os.path.join(cand, 'wavernn/models/fatchord_version.py')):
+            return cand
+    return _travel_root() or env or '/root/reference'
+
+
+REF_ROOT = _pick_root()
 REF_CKPT = os.path.join(REF_ROOT, 'logs_wavernn/checkpoints/latest_weights.pyt')
+if not os.path.isfile(REF_CKPT) and os.path.isfile(TRAVEL_CKPT):
+    REF_CKPT = TRAVEL_CKPT
 
 
 def available() -> bool:
@@ -151,3 +186,68 @@ def reference_forward_logits(model, x, mels_padded):
         out = model(torch.as_tensor(x), torch.as_tensor(mels_padded)).numpy()
     model.step.copy_(step)
     return out
+
+
+def memoize_upsample(model):
+    """bench.py's repeated bounded samples call `generate` on the SAME mel batch; the reference's conditioning network
+    (UpsampleNetwork.forward, fatchord_version.py:82-89, ~20 s for 256 x 21 frames on 8 cores) is outside the timed loop, so
+    its output -- computed by the reference's own module on first use -- is kept and handed back on later calls with an
+    identical input.  The timed sampling loop is untouched."""
+    up = model.upsample
+    if getattr(up, '_b200_memo', None) is not None:
+        return
+    orig = up.forward
+    memo = {}
+
+    def forward(m):
+        key = (tuple(m.shape), float(m.double().sum()), float(m.double().abs().max()))
+        if key not in memo:
+            memo.clear()
+            memo[key] = orig(m)
+        return memo[key]
+
+    up.forward = forward
+    up._b200_memo = memo
+
+
+class _StopSample(Exception):
+    """Raised by the step-counting hook of `timed_generate_sample` to leave the reference's loop after the sample."""
+
+
+def timed_generate_sample(model, mels, max_seconds=None, max_steps=None):
+    """Times the reference's OWN `WaveRNN.generate` loop (fatchord_version.py:201-241) on `mels` [B, 80, T] without
+    touching its code: a forward-pre-hook on `model.I` (first op of a loop step, :208) starts the clock at step 0, a
+    forward hook on `model.fc3` (last layer of a step, :223) counts completed steps and, once `max_steps` steps or
+    `max_seconds` have passed, raises to leave the loop (a bounded sample; `None` for both = the whole utterance).
+    The one-shot conditioning network (:186) runs before the clock starts and is reported separately.
+    Returns dict(steps, loop_seconds, upsample_seconds, batch)."""
+    import time
+    fv = import_reference()
+    hp = fv._hp
+    st = {'t0': None, 'n': 0, 't_end': None, 't_call': None}
+
+    def pre(_m, _inp):
+        if st['t0'] is None:
+            st['t0'] = time.perf_counter()
+
+    def post(_m, _inp, _out):
+        st['n'] += 1
+        if (max_steps is not None and st['n'] >= max_steps) or \
+                (max_seconds is not None and st['n'] % 8 == 0 and time.perf_counter() - st['t0'] >= max_seconds):
+            st['t_end'] = time.perf_counter()
+            raise _StopSample()
+
+    h1 = model.I.register_forward_pre_hook(pre)
+    h2 = model.fc3.register_forward_hook(post)
+    st['t_call'] = time.perf_counter()
+    try:
+        model.generate(torch.as_tensor(mels), '/dev/null', False, hp.voc_target, hp.voc_overlap, hp.mu_law)
+        st['t_end'] = time.perf_counter()          # ran to the end: includes the (negligible) numpy epilogue
+    except _StopSample:
+        pass
+    finally:
+        h1.remove()
+        h2.remove()
+        model.train()
+    return dict(steps=st['n'], loop_seconds=st['t_end'] - st['t0'], upsample_seconds=st['t0'] - st['t_call'],
+                batch=int(mels.shape[0]))

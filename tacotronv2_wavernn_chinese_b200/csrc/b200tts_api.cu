@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <string>
@@ -14,6 +15,7 @@
 #include "wavernn_upsample.cuh"
 #include "wavernn_utt.cuh"
 #include "wavernn_grid.cuh"
+#include "wavernn_push.cuh"
 #include "taco_decoder.cuh"
 #include "taco_encpost.cuh"
 
@@ -153,6 +155,10 @@ struct b200tts_wavernn {
   const float* d_fir = nullptr;   // [hop][NT]
   GridModel gm{};                 // per-CTA weight blobs of the grid kernel
   DeviceBuf grid_blob, mels_T, aux_T, grid_sync, grid_prof, fold_mels, fold_aux;
+  PushModel pm{};                 // small-batch push kernel (wavernn_push.cuh): per-CTA blobs + conditioning-projection weights
+  PushCondW pcw{};
+  DeviceBuf push_blob, push_condw, push_tab, push_vec, push_best, push_prof;
+  int last_push_ncta = 0;
   int* d_grid_error = nullptr;    // set by the grid kernel when a barrier wait timed out (a peer CTA vanished)
   int last_grid_ncta = 0;
   int coop = 0;
@@ -162,6 +168,7 @@ struct b200tts_wavernn {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
   int64_t launches = 0;
+  bool warned_fallback = false;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -359,6 +366,8 @@ extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b
     g.ldC = FEAT + AUX; g.ldX = R + AUX; g.ldF = F + AUX;
     g.ncta = R / kUPC;
     g.ok = (R == F) && (R % kUPC == 0) && (NC == g.ncta * kCPC) && (FEAT % 4 == 0) && (g.ncta <= ctx->sm_count);
+    // the narrow mapping stages [x1|aux], [f1|aux], [mel|aux] in a 640*G-float area and h in a 512*G-float area
+    if (R + AUX > 640 || F + AUX > 640 || FEAT + AUX > 640 || R > 512) g.ok = 0;
     int off = 0;
     auto take = [&](int n) { int o = off; off += (n + 3) & ~3; return o; };
     g.oA_w = take(16 * g.ldC); g.oA_x = take(16); g.oA_b = take(16);
@@ -425,6 +434,65 @@ extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b
       }
       ctx->grid_blob.ensure(hb.size() * sizeof(float));
       B200_CUDA(cudaMemcpy(ctx->grid_blob.p, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+      // ---- push kernel (wavernn_push.cuh): recurrent / feed-forward rows only; the conditioned columns become tables ----
+      PushModel& pm = ctx->pm;
+      pm.ncta = g.ncta; pm.R = R; pm.F = F; pm.NC = NC;
+      int poff = 0;
+      auto ptake = [&](int n) { int o = poff; poff += (n + 3) & ~3; return o; };
+      pm.ohh1 = ptake(12 * R); pm.oih2 = ptake(12 * R); pm.ohh2 = ptake(12 * R);
+      pm.ofc1 = ptake(4 * R); pm.ofc2 = ptake(4 * F); pm.ofc3 = ptake(8 * F);
+      pm.oAx = ptake(16); pm.obhh1 = ptake(12); pm.obhh2 = ptake(12); pm.obfc3 = ptake(8);
+      pm.blob = poff;
+      const size_t push_smem = ((size_t)pm.blob + (size_t)PushTraits<32>::scratch_floats(c.hop_length, NT)) * sizeof(float) + 1024;
+      pm.ok = (R == 512 && F == 512 && g.ncta == 128 && NC <= 1024 && push_smem <= 227 * 1024) ? 1 : 0;
+      if (pm.ok) {
+        std::vector<float> pb((size_t)g.ncta * pm.blob, 0.f);
+        std::vector<float> cw((size_t)g.ncta * (16 * FEAT + 36 * AUX + 36), 0.f);
+        float* wm = cw.data();
+        float* wa = wm + (size_t)g.ncta * 16 * FEAT;
+        float* cb = wa + (size_t)g.ncta * 36 * AUX;
+        for (int cta = 0; cta < g.ncta; ++cta) {
+          const float* b = &hb[(size_t)cta * g.blob];
+          float* d = &pb[(size_t)cta * pm.blob];
+          for (int r = 0; r < 12; ++r) {
+            std::memcpy(d + pm.ohh1 + (size_t)r * R, b + g.ohh1 + (size_t)r * R, sizeof(float) * R);
+            std::memcpy(d + pm.oih2 + (size_t)r * R, b + g.oih2 + (size_t)r * g.ldX, sizeof(float) * R);
+            std::memcpy(d + pm.ohh2 + (size_t)r * R, b + g.ohh2 + (size_t)r * R, sizeof(float) * R);
+            d[pm.obhh1 + r] = b[g.obhh1 + r];
+            d[pm.obhh2 + r] = b[g.obhh2 + r];
+            std::memcpy(wa + ((size_t)cta * 36 + 16 + r) * AUX, b + g.oih2 + (size_t)r * g.ldX + R, sizeof(float) * AUX);
+            cb[(size_t)cta * 36 + 16 + r] = b[g.obih2 + r];
+          }
+          for (int j = 0; j < 4; ++j) {
+            std::memcpy(d + pm.ofc1 + (size_t)j * R, b + g.ofc1 + (size_t)j * g.ldX, sizeof(float) * R);
+            std::memcpy(d + pm.ofc2 + (size_t)j * F, b + g.ofc2 + (size_t)j * g.ldF, sizeof(float) * F);
+            std::memcpy(wa + ((size_t)cta * 36 + 28 + j) * AUX, b + g.ofc1 + (size_t)j * g.ldX + R, sizeof(float) * AUX);
+            std::memcpy(wa + ((size_t)cta * 36 + 32 + j) * AUX, b + g.ofc2 + (size_t)j * g.ldF + F, sizeof(float) * AUX);
+            cb[(size_t)cta * 36 + 28 + j] = b[g.obfc1 + j];
+            cb[(size_t)cta * 36 + 32 + j] = b[g.obfc2 + j];
+          }
+          for (int r = 0; r < 8; ++r) {
+            std::memcpy(d + pm.ofc3 + (size_t)r * F, b + g.ofc3 + (size_t)r * F, sizeof(float) * F);
+            d[pm.obfc3 + r] = b[g.obfc3 + r];
+          }
+          for (int r = 0; r < 16; ++r) {          // I rows 0-3, folded GRU-1 rows 4-15: [mel | a1] columns, x coefficient, bias
+            d[pm.oAx + r] = b[g.oA_x + r];
+            std::memcpy(wm + ((size_t)cta * 16 + r) * FEAT, b + g.oA_w + (size_t)r * g.ldC, sizeof(float) * FEAT);
+            std::memcpy(wa + ((size_t)cta * 36 + r) * AUX, b + g.oA_w + (size_t)r * g.ldC + FEAT, sizeof(float) * AUX);
+            cb[(size_t)cta * 36 + r] = b[g.oA_b + r];
+          }
+        }
+        ctx->push_blob.ensure(pb.size() * sizeof(float));
+        B200_CUDA(cudaMemcpy(ctx->push_blob.p, pb.data(), pb.size() * sizeof(float), cudaMemcpyHostToDevice));
+        ctx->push_condw.ensure(cw.size() * sizeof(float));
+        B200_CUDA(cudaMemcpy(ctx->push_condw.p, cw.data(), cw.size() * sizeof(float), cudaMemcpyHostToDevice));
+        const float* cwd = ctx->push_condw.as<float>();
+        ctx->pcw.wm = cwd;
+        ctx->pcw.wa = cwd + (size_t)g.ncta * 16 * FEAT;
+        ctx->pcw.bias = ctx->pcw.wa + (size_t)g.ncta * 36 * AUX;
+        ctx->pcw.ncta = g.ncta; ctx->pcw.feat = FEAT; ctx->pcw.aux = AUX;
+      }
     }
   }
   B200_CUDA(cudaEventCreate(&ctx->ev0));
@@ -453,6 +521,12 @@ extern "C" void b200tts_wavernn_destroy(b200tts_wavernn* ctx) {
   ctx->grid_prof.release();
   ctx->fold_mels.release();
   ctx->fold_aux.release();
+  ctx->push_blob.release();
+  ctx->push_condw.release();
+  ctx->push_tab.release();
+  ctx->push_vec.release();
+  ctx->push_best.release();
+  ctx->push_prof.release();
   ctx->h_stage.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -670,6 +744,88 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   B200_CUDA(cudaEventRecord(ctx->ev1, st));
 }
 
+// ---- small-batch push kernel (wavernn_push.cuh) --------------------------------------------------------------------------
+template <int G>
+static void launch_push_t(b200tts_wavernn* ctx, PushArgs& a, cudaStream_t st) {
+  const PushModel& pm = ctx->pm;
+  using PT = PushTraits<G>;
+  size_t smem = ((size_t)pm.blob + (size_t)PT::scratch_floats(a.hop, a.NT)) * sizeof(float);
+  auto kern = wavernn_push_kernel<G>;
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPushThreads, smem));
+  REQUIRE(per_sm * ctx->sm_count >= pm.ncta, B200TTS_EINVAL, "push kernel cannot be made co-resident on this device");
+  PushModel m = pm;
+  void* args[] = {(void*)&m, (void*)&a};
+  B200_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(pm.ncta), dim3(kPushThreads), args, smem, st));
+  ctx->launches++;
+}
+
+static inline int push_rows(int B) { return B <= 4 ? 4 : (B <= 8 ? 8 : (B <= 16 ? 16 : 32)); }
+
+// Can this call take the push kernel?  (env B200TTS_PUSH=0 keeps the round-1 mappings for A/B timing.)
+static bool push_eligible(const b200tts_wavernn* ctx, int rows) {
+  static const bool off = getenv("B200TTS_PUSH") != nullptr && getenv("B200TTS_PUSH")[0] == '0';
+  return ctx->pm.ok && ctx->gm.ok && rows <= 32 && !off;
+}
+
+// `fold` != null: rows are the folds of ONE source utterance of T0 frames (conditioning tables of utterance 0, row u
+// starts at sample u * stride); otherwise row u is utterance u.
+static void launch_push(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cudaStream_t st, const FoldGeom* fold, int T0) {
+  const b200tts_wavernn_cfg& c = ctx->cfg;
+  const PushModel& pm = ctx->pm;
+  const int rows = ua.B, G = push_rows(rows);
+  const int T = fold ? T0 : ua.T, hop = c.hop_length;
+  const int tab_rows = fold ? 1 : G, src_rows = fold ? 1 : rows;
+  // conditioning tables [tab_rows][T+1][ncta][52]
+  ctx->push_tab.ensure((size_t)tab_rows * (T + 1) * pm.ncta * kPushCondRows * sizeof(float));
+  {
+    constexpr int FT = 8;
+    dim3 grid((T + 1 + FT - 1) / FT, tab_rows);
+    size_t smem = (size_t)(c.feat_dims + c.res_out_dims) * FT * sizeof(float);
+    push_cond_table_kernel<FT><<<grid, 256, smem, st>>>(ctx->pcw, d_mel, ua.aux_frames, src_rows, T, ctx->push_tab.as<float>());
+    B200_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  const size_t nvec = (size_t)kPushVecs * 2 * pm.ncta * G * 4, nbest = (size_t)pm.ncta * G;
+  ctx->push_vec.ensure(nvec * sizeof(float));
+  ctx->push_best.ensure(nbest * sizeof(unsigned long long) + 64);
+  int* d_err = reinterpret_cast<int*>(ctx->push_best.as<unsigned long long>() + nbest);
+  push_init_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->push_vec.as<uint32_t>(), nvec, ctx->push_best.as<unsigned long long>(), nbest, d_err);
+  B200_CUDA(cudaGetLastError());
+  ctx->launches++;
+  ctx->d_grid_error = d_err;
+  PushArgs a{};
+  a.wblob = ctx->push_blob.as<float>();
+  a.vec = ctx->push_vec.as<float>();
+  a.best = ctx->push_best.as<unsigned long long>();
+  a.error = d_err;
+  a.tab = ctx->push_tab.as<float>();
+  a.fir = ctx->d_fir;
+  a.NT = ctx->NT;
+  a.B = rows; a.S = ua.S; a.T = T; a.hop = hop; a.steps = ua.steps;
+  a.row_stride = fold ? fold->stride : 0;
+  a.S_src = T * hop;
+  a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.q = ua.q;
+  a.teacher = ua.teacher; a.logits_out = ua.logits_out; a.labels = ua.labels;
+  a.prof = nullptr;
+  if (getenv("B200TTS_GRID_PROF")) {
+    ctx->push_prof.ensure((size_t)pm.ncta * 12 * sizeof(long long));
+    B200_CUDA(cudaMemsetAsync(ctx->push_prof.p, 0, (size_t)pm.ncta * 12 * sizeof(long long), st));
+    a.prof = ctx->push_prof.as<long long>();
+    ctx->last_push_ncta = pm.ncta;
+    ctx->last_grid_ncta = 0;
+  }
+  B200_CUDA(cudaEventRecord(ctx->ev0, st));
+  switch (G) {
+    case 4: launch_push_t<4>(ctx, a, st); break;
+    case 8: launch_push_t<8>(ctx, a, st); break;
+    case 16: launch_push_t<16>(ctx, a, st); break;
+    default: launch_push_t<32>(ctx, a, st); break;
+  }
+  B200_CUDA(cudaEventRecord(ctx->ev1, st));
+}
+
 // After the stream has been synchronised: did the last grid launch abandon a barrier?
 static void check_grid_error(b200tts_wavernn* ctx) {
   if (!ctx->d_grid_error) return;
@@ -699,7 +855,14 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
             "T must be >= 21 frames: the reference's 20-hop fade-out (fatchord_version.py:256-258) fails below that");
   }
   int kernel = o.kernel;
-  if (kernel == B200TTS_KERNEL_AUTO) kernel = ctx->gm.ok ? B200TTS_KERNEL_GRID : B200TTS_KERNEL_UTTERANCE;
+  if (kernel == B200TTS_KERNEL_AUTO) {
+    kernel = ctx->gm.ok ? B200TTS_KERNEL_GRID : B200TTS_KERNEL_UTTERANCE;
+    if (!ctx->gm.ok && !ctx->warned_fallback) {      // never silently: this path is ~4x slower
+      ctx->warned_fallback = true;
+      fprintf(stderr, "libb200tts: these hparams / this device cannot run the weight-stationary grid kernel; kernel=auto falls "
+                      "back to the L2-streaming utterance kernel (about 4x slower at large batch)\n");
+    }
+  }
   REQUIRE(kernel == B200TTS_KERNEL_UTTERANCE || kernel == B200TTS_KERNEL_GRID, B200TTS_EINVAL, "unknown kernel selector");
   const bool folding = o.fold_target > 0;
   FoldGeom fg{};
@@ -719,8 +882,12 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
     ctx->labels.ensure((size_t)GB * GS * sizeof(int16_t));
     labels = ctx->labels.as<int16_t>();
   }
+  const bool use_push = kernel == B200TTS_KERNEL_GRID && push_eligible(ctx, GB);
+  if (kernel == B200TTS_KERNEL_GRID && !ctx->gm.ok)
+    throw Error(B200TTS_EINVAL, "kernel=grid was requested but this model/device cannot run the weight-stationary grid kernel "
+                                "(needs rnn_dims == fc_dims, n_classes == 2*rnn_dims, cooperative launch, R/4 <= SM count)");
   float* mels_up = nullptr;
-  if (kernel == B200TTS_KERNEL_UTTERANCE || folding) {
+  if (kernel == B200TTS_KERNEL_UTTERANCE || (folding && !use_push)) {
     ctx->mels_up.ensure((size_t)B * S * c.feat_dims * sizeof(float));
     mels_up = ctx->mels_up.as<float>();
   }
@@ -746,6 +913,7 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
       a.mels_up = ctx->fold_mels.as<float>();
       a.aux_frames = ctx->fold_aux.as<float>();
     }
+    ctx->d_grid_error = nullptr;
     B200_CUDA(cudaEventRecord(ctx->ev0, st));
     // utterances per CTA: enough CTAs to cover the SMs first, then amortise the L2 weight stream over more rows
     int per = (GB + ctx->sm_count - 1) / ctx->sm_count;
@@ -754,6 +922,8 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
     else if (per <= 4) launch_utt<4>(ctx, a, st);
     else launch_utt<8>(ctx, a, st);
     B200_CUDA(cudaEventRecord(ctx->ev1, st));
+  } else if (use_push) {
+    launch_push(ctx, d_mel, a, st, folding ? &fg : nullptr, T);
   } else {
     launch_grid(ctx, d_mel, a, st, folding ? &fg : nullptr, S);
   }
@@ -761,10 +931,11 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
   if (d_wave) {
     if (folding) {
       xfade_unfold_kernel<<<(wave_len + 255) / 256, 256, 0, st>>>(labels, fg.nfold, fg.L, o.fold_target, o.fold_overlap, wave_len,
-                                                                  fade_len, ctx->NC, o.mu_law, d_wave);
+                                                                  fade_len, ctx->NC, o.mu_law, ctx->d_grid_error, d_wave);
     } else {
       dim3 grid((wave_len + 255) / 256, B);
-      finish_wave_kernel<<<grid, 256, 0, st>>>(labels, S, wave_len, fade_len, ctx->NC, o.mu_law, o.d_utt_frames, hop, d_wave);
+      finish_wave_kernel<<<grid, 256, 0, st>>>(labels, S, wave_len, fade_len, ctx->NC, o.mu_law, o.d_utt_frames, hop, ctx->d_grid_error,
+                                               d_wave);
     }
     B200_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -831,19 +1002,78 @@ extern "C" int b200tts_wavernn_generate_host(b200tts_wavernn* ctx, const float* 
   API_END
 }
 
+extern "C" int b200tts_wavernn_check(b200tts_wavernn* ctx) {
+  API_BEGIN
+  REQUIRE(ctx, B200TTS_EINVAL, "null argument");
+  DeviceGuard dg(ctx->device);
+  B200_CUDA(cudaDeviceSynchronize());
+  check_grid_error(ctx);
+  API_END
+}
+
+// Register-only packed-fp32 FMA loop on every SM: the measured fp32 CUDA-core ceiling bench.py quotes the FLOP form against.
+__global__ void fp32_peak_kernel(float* out, int iters) {
+  float2 a[8], x = make_float2(1.0001f + threadIdx.x * 1e-7f, 0.9999f), y = make_float2(1e-3f, -1e-3f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = make_float2((float)i, (float)(i + 1));
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = __ffma2_rn(a[i], x, y);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+  if (s == 123.456f) out[0] = s;
+}
+extern "C" int b200tts_debug_fp32_peak(int device, double* tflops) {
+  API_BEGIN
+  REQUIRE(tflops, B200TTS_EINVAL, "null argument");
+  DeviceGuard dg(device);
+  int sms = 0;
+  B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  float* d = nullptr;
+  B200_CUDA(cudaMalloc(&d, 16));
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0));
+  B200_CUDA(cudaEventCreate(&e1));
+  const int iters = 20000, threads = 512, blocks = sms * 2;
+  fp32_peak_kernel<<<blocks, threads>>>(d, 2000);       // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    B200_CUDA(cudaEventRecord(e0));
+    fp32_peak_kernel<<<blocks, threads>>>(d, iters);
+    B200_CUDA(cudaEventRecord(e1));
+    B200_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 2.0 * 32.0 * (double)iters * blocks * threads;   // 32 FFMA2 per iteration, 2 FMAs each
+    best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  API_END
+}
+
 // Debug: per-phase cycle counters of the last grid-kernel launch (needs env B200TTS_GRID_PROF=1 at generate time).
 // out[12] = mean over CTAs of {P0 compute, P0 barrier, P1 compute, P1 barrier, ...} in SM cycles.
 extern "C" int b200tts_wavernn_debug_phase_cycles(b200tts_wavernn* ctx, double* out12) {
   API_BEGIN
-  REQUIRE(ctx && out12 && ctx->grid_prof.p && ctx->last_grid_ncta > 0, B200TTS_EINVAL, "no phase profile recorded");
+  REQUIRE(ctx && out12, B200TTS_EINVAL, "null argument");
+  const bool push = ctx->last_grid_ncta == 0 && ctx->last_push_ncta > 0 && ctx->push_prof.p;
+  REQUIRE(push || (ctx->grid_prof.p && ctx->last_grid_ncta > 0), B200TTS_EINVAL, "no phase profile recorded");
   DeviceGuard dg(ctx->device);
-  std::vector<long long> h((size_t)ctx->last_grid_ncta * 12);
+  const int n = push ? ctx->last_push_ncta : ctx->last_grid_ncta;
+  std::vector<long long> h((size_t)n * 12);
   B200_CUDA(cudaDeviceSynchronize());
-  B200_CUDA(cudaMemcpy(h.data(), ctx->grid_prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  B200_CUDA(cudaMemcpy(h.data(), push ? ctx->push_prof.p : ctx->grid_prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 12; ++i) {
     double s = 0;
-    for (int c = 0; c < ctx->last_grid_ncta; ++c) s += (double)h[(size_t)c * 12 + i];
-    out12[i] = s / ctx->last_grid_ncta;
+    for (int c = 0; c < n; ++c) s += (double)h[(size_t)c * 12 + i];
+    out12[i] = s / n;
   }
   API_END
 }

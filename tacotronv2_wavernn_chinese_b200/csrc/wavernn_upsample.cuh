@@ -168,12 +168,20 @@ __global__ void fold_cond_kernel(const float* __restrict__ mels_up, const float*
   }
 }
 
+// np.linspace(-1, 1, flen)[k]: -1 + k * 2/(flen-1), exactly +1 at the last point; a ONE point linspace is [-1]
+__device__ __forceinline__ double xfade_t(int k, int flen) {
+  if (flen <= 1) return -1.0;
+  return (k == flen - 1) ? 1.0 : (-1.0 + k * (2.0 / (flen - 1)));
+}
+
 // xfade_and_unfold (fatchord_version.py:342-405) + the generate() epilogue (:247-258), fp64:
 // decode every fold's labels, apply the equal-power fade-in/out over `overlap` (first half of the fade-in is silence),
 // overlap-add at stride target+overlap, truncate to wave_len, 20-hop linear fade-out.
 __global__ void xfade_unfold_kernel(const int16_t* __restrict__ labels /*[nfold][L]*/, int nfold, int L, int target, int overlap,
-                                    int wave_len, int fade_len, int ncls, int mu_law, double* __restrict__ wave /*[wave_len]*/) {
+                                    int wave_len, int fade_len, int ncls, int mu_law, const int* __restrict__ gen_error,
+                                    double* __restrict__ wave /*[wave_len]*/) {
   const double mu = (double)(ncls - 1);
+  const bool poisoned = gen_error && *gen_error;    // the generation kernel timed out: never hand back plausible-looking audio
   const int stride = target + overlap;
   const int silence = overlap / 2, flen = overlap - silence;
   const double lin_step = -1.0 / (double)(fade_len - 1);
@@ -193,20 +201,20 @@ __global__ void xfade_unfold_kernel(const int16_t* __restrict__ labels /*[nfold]
       // np.linspace(-1, 1, flen)[k] = -1 + k * 2/(flen-1)
       if (t < overlap) {
         double g = 0.0;
-        if (t >= silence) { const int k = t - silence; const double tt = (k == flen - 1) ? 1.0 : (-1.0 + k * (2.0 / (flen - 1))); g = sqrt(0.5 * (1.0 + tt)); }
+        if (t >= silence) { const int k = t - silence; const double tt = xfade_t(k, flen); g = sqrt(0.5 * (1.0 + tt)); }
         y *= g;
       }
       if (t >= L - overlap) {
         const int k2 = t - (L - overlap);
         double g = 1.0;
-        if (k2 >= silence) { const int k = k2 - silence; const double tt = (k == flen - 1) ? 1.0 : (-1.0 + k * (2.0 / (flen - 1))); g = sqrt(0.5 * (1.0 - tt)); }
+        if (k2 >= silence) { const int k = k2 - silence; const double tt = xfade_t(k, flen); g = sqrt(0.5 * (1.0 - tt)); }
         y *= g;
       }
       acc += y;
     }
     const int k = n - (wave_len - fade_len);
     if (k >= 0) acc *= (k == fade_len - 1) ? 0.0 : (1.0 + (double)k * lin_step);
-    wave[n] = acc;
+    wave[n] = poisoned ? nan("") : acc;
   }
 }
 
@@ -215,8 +223,9 @@ __global__ void xfade_unfold_kernel(const int16_t* __restrict__ labels /*[nfold]
 // ITS OWN (T_b - 1) * hop like a batch-1 run of the reference, and zero beyond.
 __global__ void finish_wave_kernel(const int16_t* __restrict__ labels /*[B][S]*/, int S, int wave_len_max, int fade_len,
                                    int ncls, int mu_law, const int* __restrict__ utt_frames, int hop,
-                                   double* __restrict__ wave /*[B][wave_len_max]*/) {
+                                   const int* __restrict__ gen_error, double* __restrict__ wave /*[B][wave_len_max]*/) {
   const int b = blockIdx.y;
+  const bool poisoned = gen_error && *gen_error;    // the generation kernel timed out: never hand back plausible-looking audio
   const double mu = (double)(ncls - 1);
   const double step = -1.0 / (double)(fade_len - 1);   // np.linspace(1, 0, fade_len)
   const int wave_len = utt_frames ? min(wave_len_max, max(0, (utt_frames[b] - 1) * hop)) : wave_len_max;
@@ -231,7 +240,7 @@ __global__ void finish_wave_kernel(const int16_t* __restrict__ labels /*[B][S]*/
     }
     int k = i - (wave_len - fade_len);
     if (k >= 0) y *= (k == fade_len - 1) ? 0.0 : (1.0 + (double)k * step);
-    wave[(size_t)b * wave_len_max + i] = y;
+    wave[(size_t)b * wave_len_max + i] = poisoned ? nan("") : y;
   }
 }
 

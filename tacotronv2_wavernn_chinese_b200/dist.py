@@ -44,5 +44,14 @@ def generate_sharded(generate_fn, mels, seed: int, group=None, **kw):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = mels.shape[0]
     lo, hi = shard_bounds(n, world, rank)
-    out = generate_fn(mels[lo:hi], seed=seed, utterance_offset=lo, **kw)
-    return all_gather_rows(out['labels'], n, group), (lo, hi)
+    nccl = dist.is_initialized() and dist.get_backend(group) == 'nccl'
+    dev = torch.device('cuda', torch.cuda.current_device()) if nccl else torch.device('cpu')
+    labels = generate_fn(mels[lo:hi], seed=seed, utterance_offset=lo, **kw)['labels'] if hi > lo else None
+    if world > n:
+        # fewer utterances than ranks: some ranks have nothing to generate (the engine requires B >= 1) but every rank must
+        # still take part in the collectives -- agree on the row width, then contribute a zero-row shard
+        width = torch.tensor([labels.shape[1] if labels is not None else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(width, op=dist.ReduceOp.MAX, group=group)
+        if labels is None:
+            labels = torch.zeros((0, int(width.item())), dtype=torch.int16, device=dev)
+    return all_gather_rows(labels, n, group), (lo, hi)

@@ -205,6 +205,17 @@ class WaveRNNEngine:
         _lib.check(self.lib.b200tts_wavernn_debug_phase_cycles(self._h, out))
         return np.array(list(out)).reshape(6, 2)
 
+    def check(self):
+        """Synchronises and raises if the last generate call's persistent kernel gave up waiting for a peer thread block
+        (its wave is NaN-filled in that case).  Call after the point where the caller synchronises anyway."""
+        _lib.check(self.lib.b200tts_wavernn_check(self._h))
+
+    def fp32_peak_tflops(self) -> float:
+        """Measured fp32 CUDA-core ceiling of this device (register-only FFMA2 loop), TFLOP/s."""
+        v = C.c_double()
+        _lib.check(self.lib.b200tts_debug_fp32_peak(self.device, C.byref(v)))
+        return float(v.value)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.b200tts_wavernn_launch_count(self._h))

@@ -15,7 +15,7 @@ import torch
 def synthesize_batch(synth, wavernn_engine, texts, seed=0, utterance_offset=0, kernel='auto', min_frames=21):
     """synth: tacotron.synthesizer.Synthesizer (loaded); wavernn_engine: engine.WaveRNNEngine.
     Returns (list of float64 waves, list of mels [T_b, 80])."""
-    mels, _ = synth.mels(texts, seed=seed)
+    mels, _ = synth.mels(texts, seed=seed, utterance_offset=utterance_offset)
     keep = [m for m in mels]
     T = max(max(m.shape[0] for m in keep), min_frames)
     B = len(keep)
@@ -27,5 +27,6 @@ def synthesize_batch(synth, wavernn_engine, texts, seed=0, utterance_offset=0, k
     out = wavernn_engine.generate(torch.as_tensor(batch), seed=seed, utterance_offset=utterance_offset, kernel=kernel,
                                   utt_frames=frames)
     wave = out['wave'].cpu().numpy()
+    wavernn_engine.check()
     hop = wavernn_engine.hop
     return [wave[b, :(frames[b] - 1) * hop].copy() for b in range(B)], keep

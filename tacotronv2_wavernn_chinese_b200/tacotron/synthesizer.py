@@ -45,7 +45,7 @@ class Synthesizer:
         self.engine = TacoDecoderEngine(w, device=device)
         return self
 
-    def mels(self, texts, seed=0, window=False, max_iters=None):
+    def mels(self, texts, seed=0, window=False, max_iters=None, utterance_offset=0):
         """Batch of pinyin strings -> (list of np.float32 mel [T_b, 80] scaled to [0,1] like the .npy the reference saves,
         dict with device tensors).  Each sentence decodes until its own stop token (reference graph is batch 1)."""
         seqs = [self.symbols.text_to_sequence(t) for t in texts]
@@ -57,7 +57,9 @@ class Synthesizer:
         eng = self.engine
         mem = eng.encode(ids, lengths)
         ms = int(max_iters or self.max_iters)
-        dec = eng.decode(mem, lengths, seed=seed, max_steps=ms, window=window, want_align=True)
+        # the prenet-dropout Philox stream is keyed by the GLOBAL sentence index: a sentence's mel must not depend on
+        # how the batch is sharded over ranks
+        dec = eng.decode(mem, lengths, seed=seed, utterance_offset=utterance_offset, max_steps=ms, window=window, want_align=True)
         mel = eng.postnet(dec['frames'], dec['nsteps'])
         n = dec['nsteps'].cpu().numpy()
         stop = dec['stop'].cpu().numpy()

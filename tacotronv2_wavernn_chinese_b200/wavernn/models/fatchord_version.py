@@ -169,6 +169,7 @@ class WaveRNN(nn.Module):
             raise ValueError('batched (fold-with-overlap) generation folds ONE utterance (fatchord_version.py:293-340)')
         out = eng.generate(m, seed=seed, mu_law=bool(mu_law), kernel=kernel, fold=(target, overlap) if batched else None)
         wave = out['wave'].cpu().numpy()                       # [B, wave_len] float64 (synchronises)
+        eng.check()                                            # a timed-out persistent kernel must not yield audio
         self.last_labels = out['labels']
         self.last_gen_seconds = time.time() - start
         b_size, seq_len = m.shape[0], T * self.hop_length
@@ -193,7 +194,8 @@ class WaveRNN(nn.Module):
 
     def load(self, path: Union[str, Path]):
         device = next(self.parameters()).device
-        self.load_state_dict(torch.load(path, map_location=device, weights_only=False), strict=False)
+        # a checkpoint is a plain state_dict of tensors (reference :411 saves self.state_dict()): never unpickle arbitrary objects
+        self.load_state_dict(torch.load(path, map_location=device, weights_only=True), strict=False)
         self._engine_key = None      # force a repack on next use
 
     def save(self, path: Union[str, Path]):

@@ -17,5 +17,9 @@ for k in kernels:
             ms = eng.last_kernel_ms()
         if os.environ.get('B200TTS_GRID_PROF') and k == 'grid':
             pc = eng.debug_phase_cycles() / steps
-            print('   cycles/step per phase (compute, barrier):', ' | '.join(f'P{i}: {a:.0f},{b:.0f}' for i, (a, b) in enumerate(pc)), f' total {pc.sum():.0f}')
+            if B <= 32 and os.environ.get('B200TTS_PUSH', '1') != '0':      # push kernel: 11 slots of thread 0 (see PUSH_MARK)
+                names = ['P01poll', 'P01gate', 'P2gemm', 'P2gate', 'hh1', 'P3gemm', 'P3gate+hh2', 'P4gemm', 'P4gate+cond', 'P5gemm', 'P5sample', '-']
+                print('   cycles/step:', ' '.join(f'{n}={v:.0f}' for n, v in zip(names, pc.reshape(-1))), f' total {pc.sum():.0f}')
+            else:
+                print('   cycles/step per phase (compute, barrier):', ' | '.join(f'P{i}: {a:.0f},{b:.0f}' for i, (a, b) in enumerate(pc)), f' total {pc.sum():.0f}')
         print(f'kernel={k} B={B} steps={steps}: {ms:.1f} ms -> {ms*1e3/steps:.1f} us/step, {B*steps/ms*1e3/1e6:.3f} M samples/s', flush=True)
