@@ -194,6 +194,16 @@ int b200tts_taco_decode(b200tts_taco* ctx, const float* d_memory, const int32_t*
                         const b200tts_taco_dropout* dropout, int max_steps, int window, float* d_frames, float* d_stop,
                         float* d_align, int32_t* d_nsteps, void* stream);
 
+/* Parity aid (teacher forcing): the same loop, but the COMPLETE recurrent state is reloaded from d_states before every step and
+ * the stop rule is ignored, so exactly n_steps steps run.  d_states [B][n_steps][b200tts_taco_state_floats(ctx, Tx_max)], one
+ * record per step:  x[num_mels] | context[enc_dim] | c1 | h1 | c2 | h2 [lstm_units each] | mu | max_attention | pos_rec | 0 |
+ * cumulated alignments[Tx_max] | alpha[Tx_max]   (the loop state of Architecture_wrappers.py:136-173 + attention.py:112-117).
+ * Lets a test compare EVERY step of a long, numerically chaotic run against the oracle fed with the oracle's own state. */
+int b200tts_taco_state_floats(const b200tts_taco* ctx, int Tx_max);
+int b200tts_taco_decode_forced(b200tts_taco* ctx, const float* d_memory, const int32_t* d_lengths, int B, int Tx_max,
+                               const b200tts_taco_dropout* dropout, int n_steps, int window, const float* d_states,
+                               float* d_frames, float* d_stop, float* d_align, int32_t* d_nsteps, void* stream);
+
 /* Run-once neighbours of the decoder loop (available when b200tts_taco_create also received the encoder / postnet
  * variables):
  *   b200tts_taco_encode   <- embedding lookup + EncoderConvolutions + EncoderRNN   tacotron.py:44-57, modules.py:145-217

@@ -6,8 +6,10 @@
 Same output contract: `./tacotron_inference_output/step-{step}-{md5(text)}-mel-pred.npy`, float32 (T, 80) =
 clip((mel + 4) / 8, 0, 1) (reference :114-116, :187-191), which `wavernn_gen.py --file` consumes.  Differences:
   * encoder / decoder loop / postnet run on the GPU through libb200tts.so; the TF checkpoint is read without TensorFlow.
-  * `--text` takes the space-separated pinyin the reference obtains from `get_pyin` (:187); Hanzi input needs the
-    reference's pure-Python `tacotron/pinyin` front-end on PYTHONPATH (out of scope here) -- it is used when importable.
+  * `--text` takes Hanzi (or Hanzi mixed with inline pinyin / digits / #1-#4 prosody marks) exactly like the reference: the
+    text goes through `get_pyin` (:187; restated TF-free in tacotronv2_wavernn_chinese_b200/tacotron/pinyin.py over the same two
+    public dictionaries, checked string-for-string against the reference on 300 train.txt lines).  Space separated pinyin
+    tokens pass through it unchanged, so the round-1 form `--text 'm ao2 h a2 ...'` keeps working.
   * no Griffin-Lim preview wav, no PNG plots (the alignment is saved as `...-align.npy` instead).
 """
 from __future__ import annotations
@@ -23,7 +25,7 @@ from tacotronv2_wavernn_chinese_b200.tacotron.synthesizer import Synthesizer
 
 def main(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument('--text', required=True, help='pinyin tokens separated by spaces (or Hanzi if the pinyin front-end is importable)')
+    ap.add_argument('--text', required=True, help='Hanzi sentence (or space separated pinyin tokens)')
     ap.add_argument('--checkpoint', default='logs-Tacotron-2/taco_pretrained', help='TF checkpoint prefix or directory')
     ap.add_argument('--train_txt', default=hparams.tacotron_input, help='training list the symbol table is rebuilt from')
     ap.add_argument('--symbols_json', default=None, help='JSON file with a "symbols" list (instead of scanning --train_txt)')
@@ -32,13 +34,8 @@ def main(argv=None):
     ap.add_argument('--seed', type=int, default=0, help='Philox seed of the (always on) prenet dropout')
     args = ap.parse_args(argv)
     hp = hparams.parse(args.hparams)
-    text = args.text
-    if not any(ch.isascii() and ch.isalnum() for ch in text):
-        try:
-            from tacotron.pinyin.parse_text_to_pyin import get_pyin          # the reference's front-end, if present
-            _, text = get_pyin(text)
-        except Exception as e:
-            raise SystemExit(f'Hanzi input needs the reference pinyin front-end on PYTHONPATH ({e}); pass pinyin tokens instead')
+    from tacotronv2_wavernn_chinese_b200.tacotron.pinyin import get_pyin
+    pyin, text = get_pyin(args.text)                    # reference :187: pinyin feeds the model, the normalised text names the files
     symbols = None
     if args.symbols_json:
         import json
@@ -46,7 +43,7 @@ def main(argv=None):
     synth = Synthesizer().load(args.checkpoint, hp, symbols=symbols, train_txt=args.train_txt)
     idx = hashlib.md5(text.encode('utf8')).hexdigest()
     t0 = time.time()
-    mel_path, align_path = synth.synthesize(text, args.out_dir, idx, seed=args.seed)
+    mel_path, align_path = synth.synthesize(pyin, args.out_dir, idx, seed=args.seed)
     print(f'pred_mel_path: {mel_path}')
     print(f'last: {time.time() - t0} seconds')
     return mel_path

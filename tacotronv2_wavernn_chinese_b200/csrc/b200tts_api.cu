@@ -1260,9 +1260,9 @@ extern "C" void b200tts_taco_destroy(b200tts_taco* ctx) {
   delete ctx;
 }
 
-extern "C" int b200tts_taco_decode(b200tts_taco* ctx, const float* d_memory, const int32_t* d_lengths, int B, int Tx_max,
-                                   const b200tts_taco_dropout* dropout, int max_steps, int window, float* d_frames, float* d_stop,
-                                   float* d_align, int32_t* d_nsteps, void* stream) {
+static int taco_decode_impl(b200tts_taco* ctx, const float* d_memory, const int32_t* d_lengths, int B, int Tx_max,
+                            const b200tts_taco_dropout* dropout, int max_steps, int window, const float* d_forced, float* d_frames,
+                            float* d_stop, float* d_align, int32_t* d_nsteps, void* stream) {
   API_BEGIN
   REQUIRE(ctx && d_memory && d_lengths && d_frames && d_stop && d_nsteps, B200TTS_EINVAL, "null argument");
   REQUIRE(B >= 1 && Tx_max >= 1 && Tx_max <= kTacoMaxTx && max_steps >= 1, B200TTS_EINVAL, "B, Tx_max (<= 512), max_steps out of range");
@@ -1281,6 +1281,7 @@ extern "C" int b200tts_taco_decode(b200tts_taco* ctx, const float* d_memory, con
   a.B = B; a.Tx_max = Tx_max; a.max_steps = max_steps; a.window = window;
   a.rng_mode = d.mode; a.seed = d.seed; a.utt_offset = d.utterance_offset; a.masks = d.d_masks;
   a.frames = d_frames; a.stop = d_stop; a.align = d_align; a.nsteps = d_nsteps;
+  a.forced = d_forced;
   size_t fl = 128 + w.P + (w.P + w.E + w.U) + 2 * w.U + 4 * w.U + 2 * w.U + (w.U + w.E) + w.A + 3 * kTacoMaxTx + 96 + 64 +
               (size_t)w.KW * w.NF + (size_t)w.NF * w.A + 16384;
   size_t smem = fl * sizeof(float);
@@ -1289,6 +1290,29 @@ extern "C" int b200tts_taco_decode(b200tts_taco* ctx, const float* d_memory, con
   B200_CUDA(cudaGetLastError());
   ctx->launches += 2;
   API_END
+}
+
+extern "C" int b200tts_taco_decode(b200tts_taco* ctx, const float* d_memory, const int32_t* d_lengths, int B, int Tx_max,
+                                   const b200tts_taco_dropout* dropout, int max_steps, int window, float* d_frames, float* d_stop,
+                                   float* d_align, int32_t* d_nsteps, void* stream) {
+  return taco_decode_impl(ctx, d_memory, d_lengths, B, Tx_max, dropout, max_steps, window, nullptr, d_frames, d_stop, d_align, d_nsteps,
+                          stream);
+}
+
+extern "C" int b200tts_taco_state_floats(const b200tts_taco* ctx, int Tx_max) {
+  if (!ctx || Tx_max < 1) return B200TTS_EINVAL;
+  return taco_state_floats(ctx->cfg.num_mels, ctx->cfg.enc_dim, ctx->cfg.lstm_units, Tx_max);
+}
+
+extern "C" int b200tts_taco_decode_forced(b200tts_taco* ctx, const float* d_memory, const int32_t* d_lengths, int B, int Tx_max,
+                                          const b200tts_taco_dropout* dropout, int n_steps, int window, const float* d_states,
+                                          float* d_frames, float* d_stop, float* d_align, int32_t* d_nsteps, void* stream) {
+  if (!d_states) {
+    g_err = "b200tts_taco_decode_forced needs d_states";
+    return B200TTS_EINVAL;
+  }
+  return taco_decode_impl(ctx, d_memory, d_lengths, B, Tx_max, dropout, n_steps, window, d_states, d_frames, d_stop, d_align, d_nsteps,
+                          stream);
 }
 
 extern "C" int b200tts_taco_philox_masks(int device, uint64_t seed, uint64_t utterance_offset, int B, int steps, int prenet_units,

@@ -46,7 +46,12 @@ struct TacoArgs {
   float* stop;              // [B][max_steps]
   float* align;             // [B][max_steps][Tx_max] or null
   int* nsteps;              // [B]
+  // teacher forcing (parity tests): when non-null, the COMPLETE recurrent state is reloaded from here at the start of every
+  // step and the stop rule is ignored (exactly max_steps steps run): [B][max_steps][taco_state_floats(Tx_max)] laid out as
+  //   x[mels] | ctx[E] | c1[U] | h1[U] | c2[U] | h2[U] | mu | max_att | pos_rec | 0 | cum[Tx_max] | alpha[Tx_max]
+  const float* forced;
 };
+__host__ __device__ inline int taco_state_floats(int mels, int E, int U, int Tx_max) { return mels + E + 4 * U + 4 + 2 * Tx_max; }
 
 // keys[b][t][:] = memory[b][t][:] . Wm      (BahdanauAttention memory_layer, attention.py:93-98; once per sentence)
 __global__ void taco_keys_kernel(const float* __restrict__ memory, const float* __restrict__ Wm, int rows, int E, int A,
@@ -184,6 +189,18 @@ __global__ void __launch_bounds__(kTacoThreads, 1) taco_decoder_kernel(TacoWeigh
 
   int step = 0;
   for (; step < A.max_steps; ++step) {
+    if (A.forced) {                                        // teacher forcing: reload the whole state (see TacoArgs::forced)
+      const float* st = A.forced + ((size_t)b * A.max_steps + step) * taco_state_floats(M, E, U, A.Tx_max);
+      for (int i = tid; i < M; i += kTacoThreads) x[i] = st[i];
+      for (int i = tid; i < E; i += kTacoThreads) ctxv[i] = st[M + i];
+      for (int i = tid; i < U; i += kTacoThreads) {
+        c1[i] = st[M + E + i]; h1[i] = st[M + E + U + i]; c2[i] = st[M + E + 2 * U + i]; h2[i] = st[M + E + 3 * U + i];
+      }
+      const float* tail = st + M + E + 4 * U;
+      if (tid == 0) { s_mu = tail[0]; s_max = (int)tail[1]; s_pos = (int)tail[2]; }
+      for (int i = tid; i < A.Tx_max; i += kTacoThreads) { cum[i] = tail[4 + i]; alpha[i] = tail[4 + A.Tx_max + i]; }
+      __syncthreads();
+    }
     // ---------------- prenet (2 x dense + relu + dropout 0.5, always on) ----------------
     block_matvec(W.pre1_k, W.pre1_b, x, M, P, p1, part);
     for (int j = tid; j < P; j += kTacoThreads) {
@@ -359,7 +376,7 @@ __global__ void __launch_bounds__(kTacoThreads, 1) taco_decoder_kernel(TacoWeigh
     }
     if (tid == 0) A.stop[(size_t)b * A.max_steps + step] = s_stop;
     __syncthreads();
-    if (s_stop > 0.5f) { ++step; break; }                // finished = round(stop) (half-to-even -> strictly > 0.5)
+    if (s_stop > 0.5f && !A.forced) { ++step; break; }   // finished = round(stop) (half-to-even -> strictly > 0.5)
   }
   if (tid == 0) A.nsteps[b] = step;
 }

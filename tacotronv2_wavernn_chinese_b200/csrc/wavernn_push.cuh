@@ -35,6 +35,7 @@
 //                    P5  f2 -> fc3 (8 x 512)  -> Gumbel-max over the CTA's 8 classes -> publish winner
 #pragma once
 #include "common.cuh"
+#include "wavernn_upsample.cuh"
 #include "wavernn_grid.cuh"
 
 namespace b200tts {
@@ -120,25 +121,41 @@ struct PollGuard {
   }
 };
 
-// Loads the NL float4s at base + off[i] into a[i], re-polling each one until it carries no sentinel word.
-// The LAST entry is polled alone first (a canary): consumers usually arrive before the producers have published, and
-// spinning on every entry would multiply the wasted L2 traffic by NL (at 32 rows a full pass of all 128 CTAs is 8 MB).
-template <int NL>
-__device__ __forceinline__ void poll_entries(const float* base, const int (&off)[NL], float4 (&a)[NL], PollGuard& g) {
+// ---- exchange protocol ------------------------------------------------------------------------------------------
+// If every thread spun on its own entries, 512 threads x 128 CTAs would hammer the few L2 lines of a vector with failed
+// polls (measured: 4 rows per CTA, i.e. 64 hot lines, ran SLOWER than 8 rows) and delay the very stores they wait for.
+// So ONE warp per CTA (the last one, which has no gate duties) spins on a canary -- row 0 of every producer, 4 producers
+// per lane -- while everybody else issues its loads once, optimistically, and parks at a block barrier; after the
+// barrier each thread checks what it loaded and re-polls only stragglers (rows of one producer are written by the same
+// store instruction(s) as its row 0, so there are hardly any).
+constexpr int kPushPollWarp = kPushWarps - 1;
+
+template <int G>
+__device__ __forceinline__ void canary_wait(const float* vecbase, int lane, PollGuard& g) {
+  unsigned pending = 0xFu;                       // producers lane, lane+32, lane+64, lane+96
   g.begin();
-  while (true) {
-    a[NL - 1] = ld_relaxed_f4(base + off[NL - 1]);
-    if (f4_ready(a[NL - 1]) || g.expired()) break;
+  while (pending) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (pending & (1u << i)) {
+        const float4 v = ld_relaxed_f4(vecbase + (size_t)(lane + 32 * i) * G * 4);
+        if (f4_ready(v)) pending &= ~(1u << i);
+      }
+    if (pending && g.expired()) break;
   }
-  if constexpr (NL > 1) {
+}
+
+// after the release barrier: a[i] were loaded optimistically; re-poll the ones that still carry a sentinel
+template <int NL>
+__device__ __forceinline__ void settle_entries(const float* base, const int (&off)[NL], float4 (&a)[NL], PollGuard& g) {
+  unsigned pending = 0;
 #pragma unroll
-    for (int i = 0; i < NL - 1; ++i) a[i] = ld_relaxed_f4(base + off[i]);
-    unsigned pending = 0;
-#pragma unroll
-    for (int i = 0; i < NL - 1; ++i) pending |= f4_ready(a[i]) ? 0u : (1u << i);
+  for (int i = 0; i < NL; ++i) pending |= f4_ready(a[i]) ? 0u : (1u << i);
+  if (pending) {
+    g.begin();
     while (pending && !g.aborted) {
 #pragma unroll
-      for (int i = 0; i < NL - 1; ++i)
+      for (int i = 0; i < NL; ++i)
         if (pending & (1u << i)) {
           a[i] = ld_relaxed_f4(base + off[i]);
           if (f4_ready(a[i])) pending &= ~(1u << i);
@@ -178,10 +195,12 @@ template <int G> struct PushTraits {
 };
 
 // ---- one GEMM pass: acc[ROWS][UT] over this thread's NKB producer blocks, reduced over the warp's k queues,
-//      partial sums of the 16 warps to part[(warp*ROWS + r)*G + u] -----------------------------------------------------
-template <int G, int ROWS>
-__device__ __forceinline__ void push_gemm(const float* __restrict__ W /*[ROWS][512] smem*/, const float* vecbase, float* part,
-                                          int ul, int kq, int warp, int lane, PollGuard& pg) {
+//      partial sums of the 16 warps to part[(warp*ROWS + r)*G + u].  CANARY: the vector may not have been published yet
+//      (a critical-path exchange); false for the shadow passes, whose vector travelled with one already consumed.
+//      Returns the block-wide abort flag when CANARY (the release barrier doubles as the abort vote). -------------------
+template <int G, int ROWS, bool CANARY>
+__device__ __forceinline__ int push_gemm(const float* __restrict__ W /*[ROWS][512] smem*/, const float* vecbase, float* part,
+                                         int ul, int kq, int warp, int lane, PollGuard& pg) {
   using PT = PushTraits<G>;
   constexpr int UT = PT::UT, NU = PT::NU, NKQ = PT::NKQ, NKB = PT::NKB, NL = PT::NL;
   int off[NL];
@@ -190,7 +209,15 @@ __device__ __forceinline__ void push_gemm(const float* __restrict__ W /*[ROWS][5
 #pragma unroll
     for (int j = 0; j < UT; ++j) off[i * UT + j] = ((kq + NKQ * i) * G + ul + NU * j) * 4;
   float4 a[NL];
-  poll_entries<NL>(vecbase, off, a, pg);
+#pragma unroll
+  for (int i = 0; i < NL; ++i) a[i] = ld_relaxed_f4(vecbase + off[i]);          // optimistic
+  int abort_all = 0;
+  if constexpr (CANARY) {
+    if (warp == kPushPollWarp) canary_wait<G>(vecbase, lane, pg);
+    abort_all = __syncthreads_or(pg.aborted ? 1 : 0);
+    if (abort_all) return 1;
+  }
+  settle_entries<NL>(vecbase, off, a, pg);
   float acc[ROWS][UT];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r)
@@ -203,12 +230,23 @@ __device__ __forceinline__ void push_gemm(const float* __restrict__ W /*[ROWS][5
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const float4 w = W4[r * 128 + kb];
+      if constexpr (UT == 2) {
+        // packed fp32: both rows of this thread against one broadcast weight (bit-identical to two scalar FMAs)
+        const float4 v0 = a[i * 2], v1 = a[i * 2 + 1];
+        float2 s2 = make_float2(acc[r][0], acc[r][1]);
+        s2 = __ffma2_rn(make_float2(v0.x, v1.x), make_float2(w.x, w.x), s2);
+        s2 = __ffma2_rn(make_float2(v0.y, v1.y), make_float2(w.y, w.y), s2);
+        s2 = __ffma2_rn(make_float2(v0.z, v1.z), make_float2(w.z, w.z), s2);
+        s2 = __ffma2_rn(make_float2(v0.w, v1.w), make_float2(w.w, w.w), s2);
+        acc[r][0] = s2.x; acc[r][1] = s2.y;
+      } else {
 #pragma unroll
-      for (int j = 0; j < UT; ++j) {
-        const float4 v = a[i * UT + j];
-        float s = acc[r][j];
-        s = fmaf(w.x, v.x, s); s = fmaf(w.y, v.y, s); s = fmaf(w.z, v.z, s); s = fmaf(w.w, v.w, s);
-        acc[r][j] = s;
+        for (int j = 0; j < UT; ++j) {
+          const float4 v = a[i * UT + j];
+          float s1 = acc[r][j];
+          s1 = fmaf(w.x, v.x, s1); s1 = fmaf(w.y, v.y, s1); s1 = fmaf(w.z, v.z, s1); s1 = fmaf(w.w, v.w, s1);
+          acc[r][j] = s1;
+        }
       }
     }
   }
@@ -225,6 +263,7 @@ __device__ __forceinline__ void push_gemm(const float* __restrict__ W /*[ROWS][5
 #pragma unroll
       for (int j = 0; j < UT; ++j) part[(warp * ROWS + r) * G + ul + NU * j] = acc[r][j];
   }
+  return 0;
 }
 
 template <int G, int ROWS>
@@ -236,27 +275,35 @@ __device__ __forceinline__ float push_part_sum(const float* part, int r, int u) 
 }
 
 // conditioning of step `t` for all rows -> cdst[36][G]  (rows 0-15: I rows 0-3 and folded GRU-1 rows, FIR-combined mel
-// projections + aux projection + bias; rows 16-27 GRU-2, 28-31 fc1, 32-35 fc2: aux projection + bias)
+// projections + aux projection + bias; rows 16-27 GRU-2, 28-31 fc1, 32-35 fc2: aux projection + bias).
+// All (<= 1 + kMaxTaps) table loads of an item are issued before the first FMA: one L2 round trip per item.
 template <int G>
 __device__ __forceinline__ void push_cond(const PushArgs& A, const float* fir_s, float* cdst, int c, int ncta, int t, int tid) {
+  const size_t fstride = (size_t)ncta * kPushCondRows;
+  const int fr0 = t / A.hop, ph0 = t - fr0 * A.hop;                   // row_stride == 0: every row is at the same frame / phase
   for (int it = tid; it < 36 * G; it += kPushThreads) {
-    const int r = it % 36, u = it / 36;
-    const long long n = (long long)(A.row_stride ? u * A.row_stride : 0) + t;
-    const int src = A.row_stride ? 0 : u;
-    float v;
-    if (n >= A.S_src) {                                    // beyond the source utterance: zero mel and aux -> bias only
-      v = __ldg(A.tab + (((size_t)src * (A.T + 1) + A.T) * ncta + c) * kPushCondRows + 16 + r);
-    } else {
-      const int fr = (int)(n / A.hop), ph = (int)(n % A.hop);
-      const float* row = A.tab + (((size_t)src * (A.T + 1) + fr) * ncta + c) * kPushCondRows;
-      v = __ldg(row + 16 + r);
-      if (r < 16) {
-        const size_t fstride = (size_t)ncta * kPushCondRows;
-        for (int j = 0; j < A.NT; ++j) {
-          const int f = fr + j - A.NT / 2;
-          if (f >= 0 && f < A.T) v = fmaf(fir_s[ph * A.NT + j], __ldg(row + ((ptrdiff_t)(f - fr)) * (ptrdiff_t)fstride + r), v);
-        }
+    const int u = it / 36, r = it - u * 36;
+    int src = u, fr = fr0, ph = ph0;
+    bool beyond = false;
+    if (A.row_stride) {
+      const long long n = (long long)u * A.row_stride + t;
+      src = 0;
+      beyond = n >= A.S_src;                                           // past the source utterance: zero mel and aux -> bias only
+      fr = beyond ? A.T : (int)(n / A.hop);
+      ph = beyond ? 0 : (int)(n - (long long)fr * A.hop);
+    }
+    const float* row = A.tab + (((size_t)src * (A.T + 1) + fr) * ncta + c) * kPushCondRows;
+    float v = __ldg(row + 16 + r);
+    if (r < 16 && !beyond) {
+      float pm[kMaxTaps];
+#pragma unroll
+      for (int j = 0; j < kMaxTaps; ++j) {
+        const int f = fr + j - A.NT / 2;
+        pm[j] = (j < A.NT && f >= 0 && f < A.T) ? __ldg(row + ((ptrdiff_t)(f - fr)) * (ptrdiff_t)fstride + r) : 0.f;
       }
+#pragma unroll
+      for (int j = 0; j < kMaxTaps; ++j)
+        if (j < A.NT) v = fmaf(fir_s[ph * A.NT + j], pm[j], v);        // an absent frame contributes fir * 0 = 0 exactly
     }
     cdst[r * G + u] = v;
   }
@@ -324,26 +371,42 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
     }                                            \
   } while (0)
 
+  constexpr int NCQ = kPushThreads / G, NREC = 128 / NCQ;   // winner records per thread = G/4
+  const int cq = tid / G;
   for (int t = 0; t <= A.steps; ++t) {
     const int par = t & 1;
     // ================= P01: winners of step t-1 -> label -> GRU 1 =================
+    float x = 0.f;
     if (t > 0) {
-      unsigned long long bestp = 0ull;
-      {
-        constexpr int NCQ = kPushThreads / G, NREC = 128 / NCQ;     // records per thread = G/4
-        const int cq = tid / G;
-        const unsigned long long want = (unsigned long long)((uint32_t)t & 0x3FFFFFu);
-        pg.begin();
+      const unsigned long long want = (unsigned long long)((uint32_t)t & 0x3FFFFFu);
+      unsigned long long rec[NREC];
 #pragma unroll
-        for (int i = 0; i < NREC; ++i) {
+      for (int i = 0; i < NREC; ++i) rec[i] = ld_relaxed_u64(A.best + (size_t)(cq + NCQ * i) * G + gu);     // optimistic
+      if (warp == kPushPollWarp) {                          // canary: row 0 of every producer
+        unsigned pending = 0xFu;
+        pg.begin();
+        while (pending) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if ((pending & (1u << i)) && (ld_relaxed_u64(A.best + (size_t)(lane + 32 * i) * G) & 0x3FFFFFull) == want) pending &= ~(1u << i);
+          if (pending && pg.expired()) break;
+        }
+      }
+      PUSH_MARK(0);
+      if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
+      unsigned long long bestp = 0ull;
+#pragma unroll
+      for (int i = 0; i < NREC; ++i) {
+        unsigned long long v = rec[i];
+        if ((v & 0x3FFFFFull) != want) {
           const unsigned long long* p = A.best + (size_t)(cq + NCQ * i) * G + gu;
-          unsigned long long v;
+          pg.begin();
           while (true) {
             v = ld_relaxed_u64(p);
             if ((v & 0x3FFFFFull) == want || pg.expired()) break;
           }
-          bestp = v > bestp ? v : bestp;
         }
+        bestp = v > bestp ? v : bestp;
       }
 #pragma unroll
       for (int o = G; o < 32; o <<= 1) {
@@ -351,33 +414,24 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
         bestp = other > bestp ? other : bestp;
       }
       if (lane < G) smax[warp * G + lane] = bestp;
-    }
-    PUSH_MARK(0);
-    if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
-    if (t > 0 && tid < G) {
-      unsigned long long b = 0ull;
-      // every warp covered a different set of producer CTAs: reduce the 16 warps
+      if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
+      if (gate) {                                           // every warp covered different producers: reduce the 16 warps
+        unsigned long long b = 0ull;
 #pragma unroll
-      for (int w = 0; w < kPushWarps; ++w) { const unsigned long long v = smax[w * G + tid]; b = v > b ? v : b; }
-      const int label = (int)push_cls(b);
-      const int u = tid;
-      if (u < A.B) {
-        if (c == 0) A.labels[(size_t)u * A.S + (t - 1)] = (int16_t)label;
-        const int fb = A.teacher ? (int)A.teacher[(size_t)u * A.S + (t - 1)] : label;
-        xs[u] = label_to_float(fb, ncls_m1);
-      } else {
-        xs[u] = 0.f;
+        for (int w = 0; w < kPushWarps; ++w) { const unsigned long long v = smax[w * G + gu]; b = v > b ? v : b; }
+        const int label = (int)push_cls(b);
+        if (gu < A.B) {
+          if (c == 0 && gj == 0) A.labels[(size_t)gu * A.S + (t - 1)] = (int16_t)label;
+          const int fb = A.teacher ? (int)A.teacher[(size_t)gu * A.S + (t - 1)] : label;
+          x = label_to_float(fb, ncls_m1);
+        }
       }
-    } else if (t == 0 && tid < G) {
-      xs[tid] = 0.f;
     }
     if (t == A.steps) break;                                // the extra trip only collects the last winner
-    __syncthreads();
     if (gate) {
       const float* cd = cond + par * 36 * G;
       const float* wAx = Wb + M.oAx;
       const float* bhh = Wb + M.obhh1;
-      const float x = xs[gu];
       const float iout = fmaf(wAx[gj], x, cd[gj * G + gu]);
       const float gir = fmaf(wAx[4 + gj], x, cd[(4 + gj) * G + gu]);
       const float giz = fmaf(wAx[8 + gj], x, cd[(8 + gj) * G + gu]);
@@ -389,18 +443,11 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       const size_t e = ((size_t)c * G + gu) * 4 + gj;
       st_relaxed_f32(vecp(PV_H1, par) + e, h);
       st_relaxed_f32(vecp(PV_X1, par) + e, x1own);
-      // rearm: every CTA's winner of step t-1 has been seen above, so every CTA has finished ALL its reads of the step
-      // t-1 vectors (each CTA publishes its winner last in a step) -- the other parity copy of this thread's entries can
-      // be overwritten.  Nobody polls that copy for step t+1 before it has seen THIS CTA's winner of step t, which is
-      // stored after the __syncthreads that follow this fence: the sentinels are visible gpu-wide by then.
-#pragma unroll
-      for (int v = 0; v < kPushVecs; ++v) st_relaxed_u32(vecp(v, par ^ 1) + e, kPushSentinel);
-      __threadfence();
     }
     PUSH_MARK(1);
 
     // ================= P2: GRU 2 input projection on x1(t) =================
-    push_gemm<G, 12>(Wb + M.oih2, vecp(PV_X1, par), partX, ul, kq, warp, lane, pg);
+    if (push_gemm<G, 12, true>(Wb + M.oih2, vecp(PV_X1, par), partX, ul, kq, warp, lane, pg)) return;
     PUSH_MARK(2);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (gate) {
@@ -417,13 +464,13 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
     }
     PUSH_MARK(3);
     // shadow: W_hh1 . h1(t) for step t+1
-    push_gemm<G, 12>(Wb + M.ohh1, vecp(PV_H1, par), partY, ul, kq, warp, lane, pg);
+    push_gemm<G, 12, false>(Wb + M.ohh1, vecp(PV_H1, par), partY, ul, kq, warp, lane, pg);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     for (int i = tid; i < 12 * G; i += kPushThreads) gh1[i] = push_part_sum<G, 12>(partY, i / G, i % G);
     PUSH_MARK(4);
 
     // ================= P3: fc1 + relu on x2(t) =================
-    push_gemm<G, 4>(Wb + M.ofc1, vecp(PV_X2, par), partX, ul, kq, warp, lane, pg);
+    if (push_gemm<G, 4, true>(Wb + M.ofc1, vecp(PV_X2, par), partX, ul, kq, warp, lane, pg)) return;
     PUSH_MARK(5);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (gate) {
@@ -431,26 +478,35 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       st_relaxed_f32(vecp(PV_F1, par) + ((size_t)c * G + gu) * 4 + gj, fmaxf(v, 0.f));
     }
     // shadow: W_hh2 . h2(t) for step t+1
-    push_gemm<G, 12>(Wb + M.ohh2, vecp(PV_H2, par), partY, ul, kq, warp, lane, pg);
+    push_gemm<G, 12, false>(Wb + M.ohh2, vecp(PV_H2, par), partY, ul, kq, warp, lane, pg);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     for (int i = tid; i < 12 * G; i += kPushThreads) gh2[i] = push_part_sum<G, 12>(partY, i / G, i % G);
     PUSH_MARK(6);
 
     // ================= P4: fc2 + relu on f1(t) =================
-    push_gemm<G, 4>(Wb + M.ofc2, vecp(PV_F1, par), partX, ul, kq, warp, lane, pg);
+    if (push_gemm<G, 4, true>(Wb + M.ofc2, vecp(PV_F1, par), partX, ul, kq, warp, lane, pg)) return;
     PUSH_MARK(7);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (gate) {
       const float v = push_part_sum<G, 4>(partX, gj, gu) + cond[par * 36 * G + (32 + gj) * G + gu];
-      st_relaxed_f32(vecp(PV_F2, par) + ((size_t)c * G + gu) * 4 + gj, fmaxf(v, 0.f));
+      const size_t e = ((size_t)c * G + gu) * 4 + gj;
+      st_relaxed_f32(vecp(PV_F2, par) + e, fmaxf(v, 0.f));
+      // REARM (shadow of the f2 exchange).  Every CTA's winner of step t-1 was seen at the top of this step, and a CTA
+      // publishes its winner LAST in a step: all reads of the step t-1 vectors, which live in the other parity copy, are
+      // over everywhere -- this thread's entries of that copy can take the sentinel again.  Nobody polls that copy for
+      // step t+1 before it has seen THIS CTA's winner of step t, which is stored below after two block barriers that
+      // follow this fence: the sentinels are performed gpu-wide by then.
+#pragma unroll
+      for (int v6 = 0; v6 < kPushVecs; ++v6) st_relaxed_u32(vecp(v6, par ^ 1) + e, kPushSentinel);
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
-    // shadow: conditioning of step t+1 (the other cond buffer: this step's rows have all been consumed by now except by
-    // the gate threads above, which read cond[par])
+    // shadow: conditioning of step t+1 into the other cond buffer (this step's rows 0-31 are consumed; rows 32-35 of
+    // cond[par] were read by the gate threads just above)
     if (t + 1 < A.steps) push_cond<G>(A, fir_s, cond + (par ^ 1) * 36 * G, c, ncta, t + 1, tid);
     PUSH_MARK(8);
 
     // ================= P5: fc3 on f2(t) + Gumbel-max over this CTA's 8 classes =================
-    push_gemm<G, 8>(Wb + M.ofc3, vecp(PV_F2, par), partY, ul, kq, warp, lane, pg);
+    if (push_gemm<G, 8, true>(Wb + M.ofc3, vecp(PV_F2, par), partY, ul, kq, warp, lane, pg)) return;
     PUSH_MARK(9);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (tid < 8 * G) {

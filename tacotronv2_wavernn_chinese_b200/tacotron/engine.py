@@ -55,10 +55,12 @@ class TacoDecoderEngine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def decode(self, memory, lengths=None, *, masks=None, seed=0, utterance_offset=0, max_steps=2000, window=False,
-               want_align=True):
+               want_align=True, forced_states=None):
         """memory [B, Tx, enc_dim] (tensor/ndarray); lengths [B] or None (= Tx).  masks: optional uint8 keep flags
         [B, max_steps, 2, prenet_units] (EXT mode) else Philox(seed).  Returns dict(frames [B,max_steps,80], stop
-        [B,max_steps], align [B,max_steps,Tx] or None, nsteps [B]) as CUDA tensors (rows beyond nsteps are undefined)."""
+        [B,max_steps], align [B,max_steps,Tx] or None, nsteps [B]) as CUDA tensors (rows beyond nsteps are undefined).
+        forced_states: optional [B, max_steps, state_floats(Tx)] teacher-forcing records (see include/b200tts.h,
+        b200tts_taco_decode_forced): the whole recurrent state is reloaded before every step and exactly max_steps steps run."""
         dev = self._dev()
         m = torch.as_tensor(memory).to(device=dev, dtype=torch.float32).contiguous()
         if m.dim() != 3 or m.shape[2] != self.cfg['enc_dim']:
@@ -83,13 +85,39 @@ class TacoDecoderEngine:
                     raise ValueError('masks must be [B, max_steps, 2, prenet_units]')
                 d.mode = 1
                 d.d_masks = md.data_ptr()
-            _lib.check(self.lib.b200tts_taco_decode(self._h, _ptr(m), _ptr(ln), B, Tx, C.byref(d), int(max_steps),
-                                                    1 if window else 0, _ptr(frames), _ptr(stop), _ptr(align), _ptr(nsteps),
-                                                    self._stream()))
-            for t in (m, ln, md):
+            fs = None
+            if forced_states is not None:
+                fs = torch.as_tensor(forced_states).to(device=dev, dtype=torch.float32).contiguous()
+                if tuple(fs.shape) != (B, max_steps, self.state_floats(Tx)):
+                    raise ValueError(f'forced_states must be [B, max_steps, {self.state_floats(Tx)}]')
+                _lib.check(self.lib.b200tts_taco_decode_forced(self._h, _ptr(m), _ptr(ln), B, Tx, C.byref(d), int(max_steps),
+                                                               1 if window else 0, _ptr(fs), _ptr(frames), _ptr(stop), _ptr(align),
+                                                               _ptr(nsteps), self._stream()))
+            else:
+                _lib.check(self.lib.b200tts_taco_decode(self._h, _ptr(m), _ptr(ln), B, Tx, C.byref(d), int(max_steps),
+                                                        1 if window else 0, _ptr(frames), _ptr(stop), _ptr(align), _ptr(nsteps),
+                                                        self._stream()))
+            for t in (m, ln, md, fs):
                 if t is not None:
                     t.record_stream(torch.cuda.current_stream(self.device))
         return dict(frames=frames, stop=stop, align=align, nsteps=nsteps)
+
+    def state_floats(self, Tx: int) -> int:
+        return int(self.lib.b200tts_taco_state_floats(self._h, int(Tx)))
+
+    @staticmethod
+    def pack_state(x, st, win=None, Tx_max=None):
+        """One teacher-forcing record from the oracle's loop state (oracle/tacotron_oracle.decode, capture_states):
+        x [1,80], st = dict(c1,h1,c2,h2 [1,U], ctx [1,E], alpha, cum [Tx], mu), win = dict(max_att, pos_rec)."""
+        Tx = st['alpha'].shape[0]
+        Tx_max = Tx if Tx_max is None else Tx_max
+        pad = np.zeros(Tx_max - Tx, dtype=np.float32)
+        win = win or {}
+        tail = np.array([float(st['mu']), float(win.get('max_att', 0)), float(win.get('pos_rec', 0)), 0.0], dtype=np.float32)
+        return np.concatenate([np.asarray(x, np.float32).ravel(), np.asarray(st['ctx'], np.float32).ravel(),
+                               np.asarray(st['c1'], np.float32).ravel(), np.asarray(st['h1'], np.float32).ravel(),
+                               np.asarray(st['c2'], np.float32).ravel(), np.asarray(st['h2'], np.float32).ravel(), tail,
+                               np.asarray(st['cum'], np.float32), pad, np.asarray(st['alpha'], np.float32), pad])
 
     def encode(self, ids, lengths=None):
         """ids int [B, Tx] (padded with anything beyond lengths) -> memory [B, Tx, enc_dim] (CUDA tensor)."""

@@ -8,6 +8,8 @@ import subprocess
 import sys
 
 import numpy as np
+
+from tacotronv2_wavernn_chinese_b200 import synth as synth_mod
 import pytest
 
 from conftest import ROOT
@@ -189,14 +191,40 @@ def test_fold_geometry_matches_reference_formula():
 
 
 def test_bench_cpu_arm_helpers():
-    """bench.py's CPU arm (cpu_baseline / --impl reference): same config object as the GPU arm, time-bounded batched sample."""
+    """bench.py's CPU arms (cpu_baseline / --impl reference): same config object as the GPU arm; a time-bounded sample of the
+    UNMODIFIED reference's generate loop when its travel copy is present (kind "_ref"), the numpy port beside it."""
     import argparse
     import bench
     args = argparse.Namespace(batch=4, frames=80)
-    cfg = bench.workload_config(args, 2)
+    cfg = bench.workload_config(args, 2, 'test weights')
     assert cfg['utterances_per_gpu'] == 4 and cfg['global_batch'] == 8 and cfg['steps_per_utterance'] == 80 * 275
     assert cfg['workload'].startswith('BASELINE config 3')
-    bench._BEST_THREADS = 2                                  # skip the thread probe in the test
-    rate, steps, threads = bench.cpu_oracle_rate(4, max_seconds=0.5)
-    assert rate > 0 and steps >= 10 and threads == 2
-    assert '4 utterances' in bench.cpu_sample_text(4, steps, 80)
+    bench._PORT[('t', 4)] = 2                                # skip the thread probe in the test
+    pr = bench.port_sample(4, 0.3)
+    assert pr['value'] > 0 and pr['steps'] >= 10 and pr['threads'] == 2
+    if bench.ref_model() is not None:                        # /root/reference or oracle/_ref/reference_src.zip
+        import torch
+        bench._REF[('threads', 4)] = 2
+        r = bench.ref_sample(4, 0.3)
+        assert r['value'] > 0 and r['steps'] >= 8 and r['threads'] == 2
+        base = bench.cpu_baseline(4, 80, 0.3)
+        assert base['kind'] == '_ref' and 'UNMODIFIED reference' in base['sample'] and base['port']['kind'] == 'port'
+        torch.set_num_threads(min(4, torch.get_num_threads()))
+
+
+def test_reference_travel_copy_times_the_reference_loop():
+    """oracle/ref_harness.timed_generate_sample drives the reference's OWN generate() (hooks only): step count, bounded
+    sample, and the memoised conditioning network returning what the reference module computed."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('neither /root/reference nor the travel copy oracle/_ref/reference_src.zip is present')
+    import torch
+    m = rh.build_model()
+    mel = torch.as_tensor(synth_mod.synth_mels(3, 2, 21))
+    full = rh.timed_generate_sample(m, mel, max_steps=40)
+    assert full['steps'] == 40 and full['batch'] == 2 and full['loop_seconds'] > 0
+    rh.memoize_upsample(m)
+    a = rh.timed_generate_sample(m, mel, max_steps=8)
+    b = rh.timed_generate_sample(m, mel, max_steps=8)
+    assert a['steps'] == b['steps'] == 8 and b['upsample_seconds'] < max(0.05, 0.5 * full['upsample_seconds'])
+    assert m.training                                         # generate() leaves the module in train() mode (:262)

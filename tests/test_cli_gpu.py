@@ -23,7 +23,9 @@ def test_tacotron_synthesize_then_wavernn_gen(tmp_path):
     if not (os.path.isfile(TRAVEL_COPY) and os.path.isfile(wav_ckpt)):
         pytest.skip('shipped checkpoints not available on this box')
     s = sentences()
-    text = ' '.join(s['symbols'][i] for i in s['sentences']['3']['ids'][:-1])
+    text = '宝马配挂跛骡鞍，貂蝉怨枕董翁榻。'                       # train.txt line 3 as HANZI: the CLI runs it through get_pyin (:187)
+    from tacotronv2_wavernn_chinese_b200.tacotron.pinyin import get_pyin
+    assert get_pyin(text)[0] == ' '.join(s['symbols'][i] for i in s['sentences']['3']['ids'][:-1])
     r = _run([os.path.join(ROOT, 'tacotron_synthesize.py'), '--text', text, '--checkpoint', TRAVEL_COPY,
               '--symbols_json', os.path.join(GOLDEN, 'taco_symbols.json'), '--seed', '5'], str(tmp_path))
     assert r.returncode == 0, r.stdout + r.stderr

@@ -87,6 +87,34 @@ def test_decoder_vs_oracle_real_checkpoint_config4():
     assert out['stop'].cpu().numpy()[0, n - 1] > 0.5
 
 
+@pytest.mark.parametrize('window', [False, True])
+def test_decoder_teacher_forced_all_steps_config4(window):
+    """BASELINE config 4 at the north star's bar over the WHOLE utterance: the shipped checkpoint's decoder is numerically
+    chaotic (the fp32 and fp64 oracles part ways after ~100 steps), so a free-running comparison can only hold for a prefix.
+    Teacher-forced, every step starts from the ORACLE's loop state (previous frame, LSTM c/h, context, alpha, cumulated
+    alignments, mu, window registers): each of the ~400 steps of the CUDA loop must then reproduce the oracle's frame,
+    stop token and alignments to 1e-4 / 1e-5 -- the WaveRNN side's teacher-forced logit test, for the Tacotron decoder."""
+    w = real_taco_weights()
+    if w is None:
+        pytest.skip('shipped Tacotron checkpoint not available on this box')
+    ids = sentences()['sentences']['241']['ids']
+    mem = to.encoder(w, ids)
+    masks = _masks(1238, 1, 700)
+    ref = to.decode(w, mem, dropout_masks=masks[0], max_iters=700, window=window, capture_states=range(700))
+    n = ref['n_steps']
+    assert 300 < n < 700                                   # the oracle stops by itself (405 frames without the window)
+    eng = _engine(w)
+    states = np.stack([eng.pack_state(*[ref['states'][s][i] for i in (0, 1, 3)]) for s in range(n)])[None]
+    out = eng.decode(mem[None], masks=masks[:, :n], max_steps=n, window=window, forced_states=states)
+    assert int(out['nsteps'][0]) == n
+    fr, st, al = (out[k].cpu().numpy()[0] for k in ('frames', 'stop', 'align'))
+    ferr = np.abs(fr - ref['frames']).max(axis=1)
+    assert ferr.max() <= 1e-4, f'frame error {ferr.max():.3e} at step {int(ferr.argmax())}'
+    np.testing.assert_allclose(st, ref['stop'], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(al[:, :mem.shape[0]], ref['alignments'], rtol=0, atol=1e-5)
+    assert (np.round(st) == np.round(ref['stop'])).all() and st[n - 1] > 0.5      # identical stop step
+
+
 def test_philox_dropout_replay_and_batch_invariance():
     w = synth_taco_weights(7)
     eng = _engine(w)

@@ -1,9 +1,22 @@
 set -x
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
-( timeout 300 env B200TTS_GRID_PROF=1 python tools/quick_time.py grid 1,4,8,16,32 3000 ) > gpurun_out/r02_c1_push_time.log 2>&1
-tail -20 gpurun_out/r02_c1_push_time.log
-( timeout 300 env B200TTS_PUSH=0 python tools/quick_time.py grid 1,8,32,64,128,256 3000 ) > gpurun_out/r02_c1_old_time.log 2>&1
-tail -8 gpurun_out/r02_c1_old_time.log
-( timeout 1200 python -m pytest tests/test_wavernn_gpu.py -q -x --durations=15 ) > gpurun_out/r02_c1_tests.log 2>&1
-tail -60 gpurun_out/r02_c1_tests.log
+( timeout 240 tools/exchange_bench.bin ) > gpurun_out/r02_exchange_bench.txt 2>&1
+cat gpurun_out/r02_exchange_bench.txt
+( timeout 600 python -m pytest tests/test_tacotron_gpu.py -q -x -k "teacher_forced" ) > gpurun_out/r02_c3_taco.log 2>&1
+tail -15 gpurun_out/r02_c3_taco.log
+python - <<'PY' > gpurun_out/r02_c3_e2e_diag.log 2>&1
+import time, sys, numpy as np, torch
+sys.path.insert(0, '.')
+from tacotronv2_wavernn_chinese_b200 import synth
+from tacotronv2_wavernn_chinese_b200.engine import WaveRNNEngine
+eng = WaveRNNEngine(synth.synth_state_dict(0), synth.DEFAULT_DIMS, device=0)
+m = synth.synth_mels(1, 256, 80)
+for i in range(5):
+    t0 = time.perf_counter(); r = eng.generate_host(m, seed=i); t1 = time.perf_counter()
+    print('generate_host', i, t1 - t0, 'kernel ms', eng.last_kernel_ms(), flush=True)
+md = torch.as_tensor(m).cuda()
+for i in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); r = eng.generate(md, seed=i); torch.cuda.synchronize(); t1 = time.perf_counter()
+    print('generate dev', i, t1 - t0, flush=True)
+PY
+cat gpurun_out/r02_c3_e2e_diag.log
