@@ -50,6 +50,9 @@ def parse():
     ap.add_argument('--frames', type=int, default=80)
     ap.add_argument('--kernel', default='auto', choices=('auto', 'grid', 'utterance'))
     ap.add_argument('--weights', default='auto', choices=('auto', 'shipped', 'synthetic'))
+    ap.add_argument('--workload', default='config3', choices=('config3', 'text2audio', 'tacotron'),
+                    help='config3 (default, the BASELINE metric) | text2audio: BASELINE config 5, 64 sentences text->mel->audio sharded '
+                         'over the GPUs | tacotron: BASELINE config 4, the decoder loop on the 50-token sentence')
     ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling (global batch) measurement')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -302,10 +305,142 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def _taco_setup(local):
+    """Synthesizer on the shipped Tacotron checkpoint (travel copy oracle/_ref/tacotron_weights.npz, read without TensorFlow)
+    + the 191-entry symbol table and the train.txt sentences 1-64 / 241 kept as ids in tests/golden/taco_symbols.json."""
+    from tacotronv2_wavernn_chinese_b200.tacotron.engine import TacoDecoderEngine
+    from tacotronv2_wavernn_chinese_b200.tacotron.synthesizer import Synthesizer
+    from tacotronv2_wavernn_chinese_b200.tacotron.text import Symbols
+    npz = os.path.join(ROOT, 'oracle', '_ref', 'tacotron_weights.npz')
+    if os.path.isfile(npz):
+        w = dict(np.load(npz))
+    elif os.path.isdir('/root/reference/logs-Tacotron-2/taco_pretrained'):
+        from tacotronv2_wavernn_chinese_b200.tacotron import ckpt
+        w = ckpt.load_tacotron_weights('/root/reference/logs-Tacotron-2/taco_pretrained')
+    else:
+        raise SystemExit('no Tacotron checkpoint on this box (run __graft_entry__.build() in the container first)')
+    s = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'taco_symbols.json'), encoding='utf-8'))
+    syn = Synthesizer()
+    syn.symbols = Symbols(s['symbols'])
+    syn.engine = TacoDecoderEngine(w, device=local)
+    syn.step = 206500
+    text_of = lambda k: syn.symbols.sequence_to_text(s['sentences'][str(k)]['ids'][:-1])
+    return syn, text_of, w, s
+
+
+def run_text2audio(args):
+    """BASELINE config 5: train.txt sentences 1-64 -> Tacotron-2 -> WaveRNN, one process per GPU, sentences dealt round-robin by
+    length, length-sorted chunks per launch (pipeline.synthesize_sharded).  value = audio samples of all 64 sentences / wall time
+    of the whole text->audio call (max over ranks), host strings in, host float64 waves out."""
+    import torch
+    import torch.distributed as dist
+    from tacotronv2_wavernn_chinese_b200 import synth
+    from tacotronv2_wavernn_chinese_b200.engine import WaveRNNEngine
+    from tacotronv2_wavernn_chinese_b200.pipeline import deal_round_robin, padded_lockstep_rows, plan_chunks, synthesize_sharded
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    syn, text_of, _, _ = _taco_setup(local)
+    sd, wdesc = load_weights(args.weights)
+    voc = WaveRNNEngine(sd, synth.DEFAULT_DIMS, device=local)
+    texts = [text_of(k) for k in range(1, 65)]
+    times, waves, mels = [], None, None
+    for i in range(args.warmup + args.steps):
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        waves, mels = synthesize_sharded(syn, voc, texts, seed=7)
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if i >= args.warmup:
+            times.append(float(dt.item()))
+    if rank == 0:
+        total = int(sum(len(w) for w in waves))
+        frames = [int(m.shape[0]) for m in mels]
+        shares = deal_round_robin(frames, world)
+        done = need = 0
+        for sh in shares:
+            d, n = padded_lockstep_rows([frames[i] for i in sh], plan_chunks([frames[i] for i in sh], 32))
+            done, need = done + d, need + n
+        dt = float(np.mean(times))
+        print(json.dumps({
+            'metric': 'text_to_audio_samples_per_sec', 'value': total / dt, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * dt, 'higher_is_better': True, 'scaling': 'strong', 'dtype': 'f32',
+            'data': 'train.txt sentences 1-64 (pinyin ids from tests/golden/taco_symbols.json), shipped Tacotron checkpoint, ' + wdesc,
+            'config': {'workload': 'BASELINE config 5: tacotron_synthesize -> wavernn_gen in process, 64 sentences', 'sentences': 64,
+                       'audio_seconds': total / 22050.0, 'mel_frames_min_max': [min(frames), max(frames)],
+                       'parallelism': f'sentences dealt round-robin by length over {world} GPU(s), length-sorted chunks of <= 32 rows per launch',
+                       'scheduler_rowsteps_computed_over_needed': done / max(1, need)},
+            'rtf': dt / (total / 22050.0)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_tacotron(args):
+    """BASELINE config 4: Tacotron-2 forward-attention decoder on the 50-token sentence (train.txt line 241): one step = encoder +
+    the whole decoder loop (until its stop token) + postnet on one GPU.  value = decoder steps (mel frames) per second.
+    Roofline: all decoder weights once per step = 6.9 MB, streamed from L2 by the one-CTA-per-sentence kernel."""
+    import torch
+    from oracle import tacotron_oracle as to
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    torch.cuda.set_device(local)
+    syn, text_of, w, s = _taco_setup(local)
+    text = text_of(241)
+    nst, times = 0, []
+    for i in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mels, info = syn.mels([text], seed=1238, max_iters=800)
+        torch.cuda.synchronize()
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+        nst = int(info['decode']['nsteps'][0])
+    dt = float(np.mean(times))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    step_bytes = 4 * sum(int(np.prod(v.shape)) for k, v in w.items() if k.startswith('decoder/'))
+    line = {'metric': 'tacotron_decoder_steps_per_sec', 'value': nst / dt, 'unit': 'mel frames/s', 'n_gpus': 1, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * dt, 'higher_is_better': True, 'dtype': 'f32', 'scaling': 'replicas only',
+            'data': 'train.txt line 241 (50 pinyin tokens + EOS), shipped checkpoint step 206500',
+            'config': {'workload': 'BASELINE config 4: Tacotron-2 decoder inference, 50-token sentence, 1 GPU', 'decoder_steps': nst},
+            'us_per_decoder_step': 1e6 * dt / max(1, nst),
+            'roofline': {'bound': 'hbm', 'achieved': step_bytes * nst / dt / 1e9, 'peak': float(peaks.get('hbm_gbs', 6650.0)), 'unit': 'GB/s',
+                         'frac': step_bytes * nst / dt / 1e9 / float(peaks.get('hbm_gbs', 6650.0)), 'traffic': None,
+                         'algorithmic_bytes_per_step': step_bytes,
+                         'note': 'one CTA per sentence streams the 6.9 MB of decoder weights from L2 every step; HBM sees them once'}}
+    if not args.no_cpu_baseline:
+        mem = to.encoder(w, s['sentences']['241']['ids'])
+        t0 = time.perf_counter()
+        d = to.decode(w, mem, seed=1238, max_iters=800)
+        cpu = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': d['n_steps'] / cpu, 'unit': 'mel frames/s', 'cores': 1, 'kind': 'port',
+                                'sample': f"the whole decoder loop ({d['n_steps']} steps) of the numpy oracle (TensorFlow 1.14, which the "
+                                          f"reference needs, cannot run here)"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.workload == 'text2audio':
+        return run_text2audio(args)
+    if args.workload == 'tacotron':
+        return run_tacotron(args)
     import torch
     import torch.distributed as dist
     from tacotronv2_wavernn_chinese_b200 import synth

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200TTS_ABI_VERSION 1
+#define B200TTS_ABI_VERSION 2
 
 enum {
   B200TTS_OK = 0,
@@ -82,6 +82,8 @@ typedef struct {
   uint64_t seed;
   uint64_t utterance_offset; /* global index of row 0 (multi-GPU shards keep results independent of the split) */
   const float* d_q;          /* EXT_EXPONENTIAL only */
+  const uint64_t* d_utterance_ids; /* optional [B] (ABI 2): global index of EVERY row, for batches whose rows are not consecutive
+                                      utterances (length-sorted chunks of a ragged set, pipeline.py); overrides utterance_offset */
 } b200tts_rng;
 
 enum {

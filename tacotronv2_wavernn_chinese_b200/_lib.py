@@ -37,7 +37,8 @@ class Tensor(C.Structure):
 
 
 class Rng(C.Structure):
-    _fields_ = [('mode', C.c_int32), ('seed', C.c_uint64), ('utterance_offset', C.c_uint64), ('d_q', C.c_void_p)]
+    _fields_ = [('mode', C.c_int32), ('seed', C.c_uint64), ('utterance_offset', C.c_uint64), ('d_q', C.c_void_p),
+                ('d_utterance_ids', C.c_void_p)]
 
 
 class GenOpts(C.Structure):
@@ -110,7 +111,7 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
-            if lib.b200tts_abi_version() != 1:
+            if lib.b200tts_abi_version() != 2:
                 raise RuntimeError('libb200tts.so ABI version mismatch; rebuild it')
             _lib = lib
     return _lib

@@ -719,7 +719,7 @@ static void launch_grid(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   a.mels_T = ctx->mels_T.as<float>();
   a.aux_T = ctx->aux_T.as<float>();
   a.B = B; a.Bp = Bp; a.S = S; a.T = T; a.hop = ua.hop; a.steps = ua.steps;
-  a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.q = ua.q;
+  a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.utt_ids = ua.utt_ids; a.q = ua.q;
   a.teacher = ua.teacher; a.logits_out = ua.logits_out; a.labels = ua.labels;
   a.prof = nullptr;
   if (getenv("B200TTS_GRID_PROF")) {
@@ -761,7 +761,11 @@ static void launch_push_t(b200tts_wavernn* ctx, PushArgs& a, cudaStream_t st) {
   ctx->launches++;
 }
 
-static inline int push_rows(int B) { return B <= 4 ? 4 : (B <= 8 ? 8 : (B <= 16 ? 16 : 32)); }
+static inline int push_rows(int B) {
+  static const int min_g = getenv("B200TTS_PUSH_MIN_G") ? atoi(getenv("B200TTS_PUSH_MIN_G")) : 4;   // A/B switch (timing only)
+  const int g = B <= 4 ? 4 : (B <= 8 ? 8 : (B <= 16 ? 16 : 32));
+  return g < min_g ? (min_g <= 8 ? 8 : (min_g <= 16 ? 16 : 32)) : g;
+}
 
 // Can this call take the push kernel?  (env B200TTS_PUSH=0 keeps the round-1 mappings for A/B timing.)
 static bool push_eligible(const b200tts_wavernn* ctx, int rows) {
@@ -806,7 +810,7 @@ static void launch_push(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   a.B = rows; a.S = ua.S; a.T = T; a.hop = hop; a.steps = ua.steps;
   a.row_stride = fold ? fold->stride : 0;
   a.S_src = T * hop;
-  a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.q = ua.q;
+  a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.utt_ids = ua.utt_ids; a.q = ua.q;
   a.teacher = ua.teacher; a.logits_out = ua.logits_out; a.labels = ua.labels;
   a.prof = nullptr;
   if (getenv("B200TTS_GRID_PROF")) {
@@ -898,6 +902,8 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
   a.aux_frames = ctx->aux_frames.as<float>();
   a.B = GB; a.S = GS; a.T = folding ? GS : T; a.hop = folding ? 1 : hop; a.steps = folding ? GS : steps;
   a.rng_mode = r.mode; a.seed = r.seed; a.utt_offset = r.utterance_offset; a.q = r.d_q;
+  a.utt_ids = reinterpret_cast<const unsigned long long*>(r.d_utterance_ids);
+  REQUIRE(!(folding && r.d_utterance_ids), B200TTS_EINVAL, "d_utterance_ids cannot be combined with fold-with-overlap generation");
   a.teacher = o.d_teacher; a.logits_out = o.d_logits; a.labels = labels;
 
   if (kernel == B200TTS_KERNEL_UTTERANCE) {

@@ -72,6 +72,7 @@ struct GridArgs {
   int B, Bp, S, T, hop, steps;
   int rng_mode;
   unsigned long long seed, utt_offset;
+  const unsigned long long* utt_ids;   // optional [B]: global utterance index of every row (overrides utt_offset + row)
   const float* q;              // [S][B][NC]
   const int16_t* teacher;      // [B][S]
   float* logits_out;           // [S][B][NC]
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(MapTraits<U, UW, GROUPS>::NW * 32, 1) wavernn_
             float q[4];
             const int cls0 = c * kCPC + r4 * 4;
             if (A.rng_mode == 0) {
-              philox_exp4(A.seed, A.utt_offset + (unsigned long long)u, (uint32_t)t, (uint32_t)(cls0 >> 2), q);
+              philox_exp4(A.seed, A.utt_ids ? A.utt_ids[u] : A.utt_offset + (unsigned long long)u, (uint32_t)t, (uint32_t)(cls0 >> 2), q);
             } else {
               float4 qv = __ldg(reinterpret_cast<const float4*>(A.q + ((size_t)t * A.B + u) * M.NC + cls0));
               q[0] = qv.x; q[1] = qv.y; q[2] = qv.z; q[3] = qv.w;

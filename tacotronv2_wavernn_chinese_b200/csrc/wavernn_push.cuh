@@ -70,6 +70,7 @@ struct PushArgs {
   int S_src;                     // samples of the source utterance (conditioning is ZERO beyond, fatchord_version.py:315-317)
   int rng_mode;
   unsigned long long seed, utt_offset;
+  const unsigned long long* utt_ids;   // optional [B]: global utterance index of every row (overrides utt_offset + row)
   const float* q;                // [S][B][NC]
   const int16_t* teacher;        // [B][S]
   float* logits_out;             // [S][B][NC]
@@ -122,32 +123,15 @@ struct PollGuard {
 };
 
 // ---- exchange protocol ------------------------------------------------------------------------------------------
-// If every thread spun on its own entries, 512 threads x 128 CTAs would hammer the few L2 lines of a vector with failed
-// polls (measured: 4 rows per CTA, i.e. 64 hot lines, ran SLOWER than 8 rows) and delay the very stores they wait for.
-// So ONE warp per CTA (the last one, which has no gate duties) spins on a canary -- row 0 of every producer, 4 producers
-// per lane -- while everybody else issues its loads once, optimistically, and parks at a block barrier; after the
-// barrier each thread checks what it loaded and re-polls only stragglers (rows of one producer are written by the same
-// store instruction(s) as its row 0, so there are hardly any).
-constexpr int kPushPollWarp = kPushWarps - 1;
-
-template <int G>
-__device__ __forceinline__ void canary_wait(const float* vecbase, int lane, PollGuard& g) {
-  unsigned pending = 0xFu;                       // producers lane, lane+32, lane+64, lane+96
-  g.begin();
-  while (pending) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (pending & (1u << i)) {
-        const float4 v = ld_relaxed_f4(vecbase + (size_t)(lane + 32 * i) * G * 4);
-        if (f4_ready(v)) pending &= ~(1u << i);
-      }
-    if (pending && g.expired()) break;
-  }
-}
-
-// after the release barrier: a[i] were loaded optimistically; re-poll the ones that still carry a sentinel
+// Measured in isolation (tools/exchange_bench.cu -> profiles/r02_exchange_bench.txt, cycles per all-to-all exchange of
+// a [128][G][4] vector by 128 CTAs, G = 4 / 8 / 32):  counter barrier + loads 3511 / 3600 / 4106;  every thread
+// spinning on its own entries 1558 / 2033 / 4140;  one canary warp (on the data or on replicated hint words) releasing
+// the block through a barrier 2928-3761 / 3780-4545 / 6754-7465.  The direct spin wins: detection and delivery are the
+// same L2 round trip.  Every thread issues ALL its loads first and re-polls only what still carries a sentinel.
 template <int NL>
-__device__ __forceinline__ void settle_entries(const float* base, const int (&off)[NL], float4 (&a)[NL], PollGuard& g) {
+__device__ __forceinline__ void poll_entries(const float* base, const int (&off)[NL], float4 (&a)[NL], PollGuard& g) {
+#pragma unroll
+  for (int i = 0; i < NL; ++i) a[i] = ld_relaxed_f4(base + off[i]);
   unsigned pending = 0;
 #pragma unroll
   for (int i = 0; i < NL; ++i) pending |= f4_ready(a[i]) ? 0u : (1u << i);
@@ -180,7 +164,7 @@ template <int G> struct PushTraits {
   static constexpr int NKB = 128 / NKQ;                    // producer blocks (float4 columns) per thread and row
   static constexpr int NL = NKB * UT;                      // float4 loads per thread and vector = G/4
   static constexpr int kPartFloats = kPushWarps * 12 * G;
-  static_assert(NU >= 4 && NU <= 32 && NKQ * NKB == 128 && NL * 4 == G, "mapping");
+  static_assert(NU >= 4 && NU <= 32 && NKQ * NKB == 128 && NL * 4 == G && (32 / NU) * NKB == 8 && (NKB == 1 || NKB == 2 || NKB == 4), "mapping");
   // shared memory after the weight blob (floats)
   static constexpr int oPartX = 0;
   static constexpr int oPartY = oPartX + kPartFloats;
@@ -194,63 +178,54 @@ template <int G> struct PushTraits {
   static constexpr int scratch_floats(int hop, int NT) { return oFir + ((hop * NT + 3) & ~3); }
 };
 
-// ---- one GEMM pass: acc[ROWS][UT] over this thread's NKB producer blocks, reduced over the warp's k queues,
-//      partial sums of the 16 warps to part[(warp*ROWS + r)*G + u].  CANARY: the vector may not have been published yet
-//      (a critical-path exchange); false for the shadow passes, whose vector travelled with one already consumed.
-//      Returns the block-wide abort flag when CANARY (the release barrier doubles as the abort vote). -------------------
-template <int G, int ROWS, bool CANARY>
-__device__ __forceinline__ int push_gemm(const float* __restrict__ W /*[ROWS][512] smem*/, const float* vecbase, float* part,
-                                         int ul, int kq, int warp, int lane, PollGuard& pg) {
+// ---- one GEMM pass over this thread's NKB producer blocks x UT rows.  The 128 four-term dot products of an output (one
+//      per producer block kb) are combined in ONE fixed order for every G: pairwise by bit 0, 1, 2 of kb (inside the thread
+//      while it owns the pair, by warp shuffle otherwise; 8 consecutive kb per warp for every G), then the 16 warps in
+//      sequence (push_part_sum).  A row's result is therefore bit-identical whatever batch it is generated in (G = 4 ... 32),
+//      which is what lets N ranks reproduce the single-rank labels exactly.  Partials to part[(warp*ROWS + r)*G + u]. -------
+template <int G, int ROWS>
+__device__ __forceinline__ void push_gemm(const float* __restrict__ W /*[ROWS][512] smem*/, const float* vecbase, float* part,
+                                          int ul, int kq, int warp, int lane, PollGuard& pg) {
   using PT = PushTraits<G>;
-  constexpr int UT = PT::UT, NU = PT::NU, NKQ = PT::NKQ, NKB = PT::NKB, NL = PT::NL;
+  constexpr int UT = PT::UT, NU = PT::NU, NKB = PT::NKB, NL = PT::NL;
   int off[NL];
 #pragma unroll
   for (int i = 0; i < NKB; ++i)
 #pragma unroll
-    for (int j = 0; j < UT; ++j) off[i * UT + j] = ((kq + NKQ * i) * G + ul + NU * j) * 4;
+    for (int j = 0; j < UT; ++j) off[i * UT + j] = ((kq * NKB + i) * G + ul + NU * j) * 4;
   float4 a[NL];
-#pragma unroll
-  for (int i = 0; i < NL; ++i) a[i] = ld_relaxed_f4(vecbase + off[i]);          // optimistic
-  int abort_all = 0;
-  if constexpr (CANARY) {
-    if (warp == kPushPollWarp) canary_wait<G>(vecbase, lane, pg);
-    abort_all = __syncthreads_or(pg.aborted ? 1 : 0);
-    if (abort_all) return 1;
-  }
-  settle_entries<NL>(vecbase, off, a, pg);
+  poll_entries<NL>(vecbase, off, a, pg);
   float acc[ROWS][UT];
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-    for (int j = 0; j < UT; ++j) acc[r][j] = 0.f;
   const float4* W4 = reinterpret_cast<const float4*>(W);
 #pragma unroll
-  for (int i = 0; i < NKB; ++i) {
-    const int kb = kq + NKQ * i;
+  for (int r = 0; r < ROWS; ++r) {
+    float leaf[NKB][UT];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const float4 w = W4[r * 128 + kb];
+    for (int i = 0; i < NKB; ++i) {
+      const float4 w = W4[r * 128 + kq * NKB + i];
       if constexpr (UT == 2) {
-        // packed fp32: both rows of this thread against one broadcast weight (bit-identical to two scalar FMAs)
+        // packed fp32: both rows of this thread against one broadcast weight (bit-identical to two scalar FMA chains)
         const float4 v0 = a[i * 2], v1 = a[i * 2 + 1];
-        float2 s2 = make_float2(acc[r][0], acc[r][1]);
-        s2 = __ffma2_rn(make_float2(v0.x, v1.x), make_float2(w.x, w.x), s2);
+        float2 s2 = __ffma2_rn(make_float2(v0.x, v1.x), make_float2(w.x, w.x), make_float2(0.f, 0.f));
         s2 = __ffma2_rn(make_float2(v0.y, v1.y), make_float2(w.y, w.y), s2);
         s2 = __ffma2_rn(make_float2(v0.z, v1.z), make_float2(w.z, w.z), s2);
         s2 = __ffma2_rn(make_float2(v0.w, v1.w), make_float2(w.w, w.w), s2);
-        acc[r][0] = s2.x; acc[r][1] = s2.y;
+        leaf[i][0] = s2.x; leaf[i][1] = s2.y;
       } else {
-#pragma unroll
-        for (int j = 0; j < UT; ++j) {
-          const float4 v = a[i * UT + j];
-          float s1 = acc[r][j];
-          s1 = fmaf(w.x, v.x, s1); s1 = fmaf(w.y, v.y, s1); s1 = fmaf(w.z, v.z, s1); s1 = fmaf(w.w, v.w, s1);
-          acc[r][j] = s1;
-        }
+        const float4 v = a[i];
+        float s1 = fmaf(w.x, v.x, 0.f);
+        s1 = fmaf(w.y, v.y, s1); s1 = fmaf(w.z, v.z, s1); s1 = fmaf(w.w, v.w, s1);
+        leaf[i][0] = s1;
       }
     }
+#pragma unroll
+    for (int j = 0; j < UT; ++j) {
+      if constexpr (NKB == 4) acc[r][j] = (leaf[0][j] + leaf[1][j]) + (leaf[2][j] + leaf[3][j]);
+      else if constexpr (NKB == 2) acc[r][j] = leaf[0][j] + leaf[1][j];
+      else acc[r][j] = leaf[0][j];
+    }
   }
-  // k queues that share a warp: lanes ul + NU*m
+  // the remaining levels of the 8-block tree: k queues that share the warp sit at lanes ul + NU*m
 #pragma unroll
   for (int o = NU; o < 32; o <<= 1)
 #pragma unroll
@@ -263,7 +238,6 @@ __device__ __forceinline__ int push_gemm(const float* __restrict__ W /*[ROWS][51
 #pragma unroll
       for (int j = 0; j < UT; ++j) part[(warp * ROWS + r) * G + ul + NU * j] = acc[r][j];
   }
-  return 0;
 }
 
 template <int G, int ROWS>
@@ -381,19 +355,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       const unsigned long long want = (unsigned long long)((uint32_t)t & 0x3FFFFFu);
       unsigned long long rec[NREC];
 #pragma unroll
-      for (int i = 0; i < NREC; ++i) rec[i] = ld_relaxed_u64(A.best + (size_t)(cq + NCQ * i) * G + gu);     // optimistic
-      if (warp == kPushPollWarp) {                          // canary: row 0 of every producer
-        unsigned pending = 0xFu;
-        pg.begin();
-        while (pending) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if ((pending & (1u << i)) && (ld_relaxed_u64(A.best + (size_t)(lane + 32 * i) * G) & 0x3FFFFFull) == want) pending &= ~(1u << i);
-          if (pending && pg.expired()) break;
-        }
-      }
-      PUSH_MARK(0);
-      if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
+      for (int i = 0; i < NREC; ++i) rec[i] = ld_relaxed_u64(A.best + (size_t)(cq + NCQ * i) * G + gu);
       unsigned long long bestp = 0ull;
 #pragma unroll
       for (int i = 0; i < NREC; ++i) {
@@ -408,6 +370,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
         }
         bestp = v > bestp ? v : bestp;
       }
+      PUSH_MARK(0);
 #pragma unroll
       for (int o = G; o < 32; o <<= 1) {
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, bestp, o);
@@ -444,10 +407,11 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       st_relaxed_f32(vecp(PV_H1, par) + e, h);
       st_relaxed_f32(vecp(PV_X1, par) + e, x1own);
     }
+    __syncwarp();      // (4G < 32: lanes that skip the gate block must not run ahead into a spin loop and steal its issue slots)
     PUSH_MARK(1);
 
     // ================= P2: GRU 2 input projection on x1(t) =================
-    if (push_gemm<G, 12, true>(Wb + M.oih2, vecp(PV_X1, par), partX, ul, kq, warp, lane, pg)) return;
+    push_gemm<G, 12>(Wb + M.oih2, vecp(PV_X1, par), partX, ul, kq, warp, lane, pg);
     PUSH_MARK(2);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (gate) {
@@ -462,29 +426,31 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       st_relaxed_f32(vecp(PV_H2, par) + e, h);
       st_relaxed_f32(vecp(PV_X2, par) + e, x1own + h);
     }
+    __syncwarp();
     PUSH_MARK(3);
     // shadow: W_hh1 . h1(t) for step t+1
-    push_gemm<G, 12, false>(Wb + M.ohh1, vecp(PV_H1, par), partY, ul, kq, warp, lane, pg);
+    push_gemm<G, 12>(Wb + M.ohh1, vecp(PV_H1, par), partY, ul, kq, warp, lane, pg);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     for (int i = tid; i < 12 * G; i += kPushThreads) gh1[i] = push_part_sum<G, 12>(partY, i / G, i % G);
     PUSH_MARK(4);
 
     // ================= P3: fc1 + relu on x2(t) =================
-    if (push_gemm<G, 4, true>(Wb + M.ofc1, vecp(PV_X2, par), partX, ul, kq, warp, lane, pg)) return;
+    push_gemm<G, 4>(Wb + M.ofc1, vecp(PV_X2, par), partX, ul, kq, warp, lane, pg);
     PUSH_MARK(5);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (gate) {
       const float v = push_part_sum<G, 4>(partX, gj, gu) + cond[par * 36 * G + (28 + gj) * G + gu];
       st_relaxed_f32(vecp(PV_F1, par) + ((size_t)c * G + gu) * 4 + gj, fmaxf(v, 0.f));
     }
+    __syncwarp();
     // shadow: W_hh2 . h2(t) for step t+1
-    push_gemm<G, 12, false>(Wb + M.ohh2, vecp(PV_H2, par), partY, ul, kq, warp, lane, pg);
+    push_gemm<G, 12>(Wb + M.ohh2, vecp(PV_H2, par), partY, ul, kq, warp, lane, pg);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     for (int i = tid; i < 12 * G; i += kPushThreads) gh2[i] = push_part_sum<G, 12>(partY, i / G, i % G);
     PUSH_MARK(6);
 
     // ================= P4: fc2 + relu on f1(t) =================
-    if (push_gemm<G, 4, true>(Wb + M.ofc2, vecp(PV_F1, par), partX, ul, kq, warp, lane, pg)) return;
+    push_gemm<G, 4>(Wb + M.ofc2, vecp(PV_F1, par), partX, ul, kq, warp, lane, pg);
     PUSH_MARK(7);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (gate) {
@@ -500,13 +466,14 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       for (int v6 = 0; v6 < kPushVecs; ++v6) st_relaxed_u32(vecp(v6, par ^ 1) + e, kPushSentinel);
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
+    __syncwarp();
     // shadow: conditioning of step t+1 into the other cond buffer (this step's rows 0-31 are consumed; rows 32-35 of
     // cond[par] were read by the gate threads just above)
     if (t + 1 < A.steps) push_cond<G>(A, fir_s, cond + (par ^ 1) * 36 * G, c, ncta, t + 1, tid);
     PUSH_MARK(8);
 
     // ================= P5: fc3 on f2(t) + Gumbel-max over this CTA's 8 classes =================
-    if (push_gemm<G, 8, true>(Wb + M.ofc3, vecp(PV_F2, par), partY, ul, kq, warp, lane, pg)) return;
+    push_gemm<G, 8>(Wb + M.ofc3, vecp(PV_F2, par), partY, ul, kq, warp, lane, pg);
     PUSH_MARK(9);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (tid < 8 * G) {
@@ -517,7 +484,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       if (u < A.B) {
         if (A.rng_mode == 0) {
           float q4[4];
-          philox_exp4(A.seed, A.utt_offset + (unsigned long long)u, (uint32_t)t, (uint32_t)(cls >> 2), q4);
+          philox_exp4(A.seed, A.utt_ids ? A.utt_ids[u] : A.utt_offset + (unsigned long long)u, (uint32_t)t, (uint32_t)(cls >> 2), q4);
           qv = q4[cls & 3];
         } else {
           qv = __ldg(A.q + ((size_t)t * A.B + u) * M.NC + cls);
@@ -533,6 +500,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       for (int r = 1; r < 8; ++r) { const unsigned long long v = skeys[r * G + tid]; b = v > b ? v : b; }
       st_relaxed_u64(A.best + (size_t)c * G + tid, b);
     }
+    __syncwarp();
     PUSH_MARK(10);
   }
   if (A.prof && tid == 0)

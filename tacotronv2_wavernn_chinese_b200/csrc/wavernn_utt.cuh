@@ -39,6 +39,7 @@ struct GenArgs {
   int steps;                  // number of steps to run (<= S)
   int rng_mode;
   unsigned long long seed, utt_offset;
+  const unsigned long long* utt_ids;   // optional [B]: global utterance index of every row (overrides utt_offset + row)
   const float* q;             // [S][B][NC] (EXT_EXPONENTIAL)
   const int16_t* teacher;     // [B][S] or null
   float* logits_out;          // [S][B][NC] or null
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kUttThreads, 1) wavernn_utt_kernel(StepWeights
         for (int c4 = tid; c4 < NC / 4; c4 += kUttThreads) {
           float q[4];
           if (A.rng_mode == 0) {
-            philox_exp4(A.seed, A.utt_offset + (unsigned long long)b, (uint32_t)i, (uint32_t)c4, q);
+            philox_exp4(A.seed, A.utt_ids ? A.utt_ids[b] : A.utt_offset + (unsigned long long)b, (uint32_t)i, (uint32_t)c4, q);
           } else {
             float4 qv = *reinterpret_cast<const float4*>(A.q + ((size_t)i * A.B + b) * NC + c4 * 4);
             q[0] = qv.x; q[1] = qv.y; q[2] = qv.z; q[3] = qv.w;

@@ -97,7 +97,7 @@ class WaveRNNEngine:
                                                          self._stream()))
         return up, (aux if full_aux else auxf)
 
-    def generate(self, mels, *, seed: int = 0, utterance_offset: int = 0, q=None, teacher=None,
+    def generate(self, mels, *, seed: int = 0, utterance_offset: int = 0, utterance_ids=None, q=None, teacher=None,
                  return_logits: bool = False, want_wave: bool = True, mu_law: bool = True, kernel: str = 'auto',
                  max_steps: int = 0, fold=None, utt_frames=None):
         """Runs the generation loop on the device.
@@ -123,6 +123,12 @@ class WaveRNNEngine:
             rng = Rng()
             rng.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
             rng.utterance_offset = int(utterance_offset)
+            ids = None
+            if utterance_ids is not None:       # rows that are NOT consecutive utterances (length-sorted chunks): per-row global index
+                ids = torch.as_tensor(np.asarray(utterance_ids, dtype=np.int64)).to(dev).contiguous()
+                if tuple(ids.shape) != (B,) or fold is not None:
+                    raise ValueError('utterance_ids must be [B] (and cannot be combined with fold)')
+                rng.d_utterance_ids = ids.data_ptr()
             qd = None
             if q is not None:
                 qd = torch.as_tensor(q).to(device=dev, dtype=torch.float32).contiguous()
@@ -157,7 +163,7 @@ class WaveRNNEngine:
             _lib.check(self.lib.b200tts_wavernn_generate(self._h, _ptr(m), B, T, C.byref(rng), C.byref(opts),
                                                          _ptr(labels), _ptr(wave), self._stream()))
             # keep inputs alive until the stream has consumed them
-            for t in (m, qd, td, uf):
+            for t in (m, qd, td, uf, ids):
                 if t is not None:
                     t.record_stream(torch.cuda.current_stream(self.device))
         return dict(labels=labels, wave=wave, logits=logits, steps=steps)

@@ -1,32 +1,111 @@
-"""Text -> mel -> audio in one process on the GPU (BASELINE config 5).
+"""Text -> mel -> audio in one process on the GPU(s) (BASELINE config 5).
 
 The reference couples its two halves only through a `.npy` file on disk (tacotron_synthesize.py:114-116 ->
 wavernn_gen.py:22, float32 (T, 80) = clip((mel + 4) / 8, 0, 1)).  Here the same array goes straight from the Tacotron
-postnet to the WaveRNN conditioning network; ragged sentences are zero-padded to the longest mel, which leaves every
-utterance's samples identical to a batch-1 run (the conditioning network sees zero frames past the end either way), and each
-row is truncated / faded at its own length.
+postnet to the WaveRNN conditioning network.
+
+Ragged sets are scheduled, not just padded.  A lock-step costs the same whether a row still has samples to produce or not,
+and below ~32 rows it barely depends on the row count at all, so
+  * the vocoder runs LENGTH-SORTED CHUNKS of at most `max_rows` rows (one launch each, padded only to the longest mel of the
+    chunk; every row is truncated / faded at its own length, `gen_opts.d_utt_frames`) -- the padded lock-steps of a 64-sentence
+    set drop from (longest - mean) x 64 to the spread inside each chunk;
+  * across ranks the sentences are dealt round-robin in order of decreasing length, so every rank gets the same
+    length profile and the makespan is the longest sentence's;
+  * the sampling noise and the prenet dropout are keyed by the GLOBAL sentence index (`rng.d_utterance_ids`), so a
+    sentence's audio depends neither on the chunking nor on the number of ranks.
+Tacotron itself is replicated on every rank: one thread block decodes one sentence, all sentences of a set decode
+concurrently (<= 148 per GPU), so sharding it would not shorten anything -- and it removes the mel exchange.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
+import torch.distributed as dist
+
+MIN_FRAMES = 21          # shorter than the 20-hop fade-out cannot be faded (the reference raises, fatchord_version.py:256-258)
 
 
-def synthesize_batch(synth, wavernn_engine, texts, seed=0, utterance_offset=0, kernel='auto', min_frames=21):
-    """synth: tacotron.synthesizer.Synthesizer (loaded); wavernn_engine: engine.WaveRNNEngine.
-    Returns (list of float64 waves, list of mels [T_b, 80])."""
+def plan_chunks(frames, max_rows=32):
+    """Indices of `frames` grouped into launches: sorted by decreasing length, cut every `max_rows`."""
+    order = sorted(range(len(frames)), key=lambda i: (-int(frames[i]), i))
+    return [order[i:i + max_rows] for i in range(0, len(order), max_rows)]
+
+
+def deal_round_robin(frames, world):
+    """Sentence indices of every rank: the length-sorted list dealt like cards (rank r gets positions r, r+world, ...)."""
+    order = sorted(range(len(frames)), key=lambda i: (-int(frames[i]), i))
+    return [order[r::world] for r in range(world)]
+
+
+def padded_lockstep_rows(frames, chunks, hop=275):
+    """(row-steps computed, row-steps needed) of a chunk plan: the scheduler's efficiency."""
+    done = sum(len(c) * max(max(int(frames[i]) for i in c), MIN_FRAMES) for c in chunks) * hop
+    need = sum(max(int(f), MIN_FRAMES) for f in frames) * hop
+    return done, need
+
+
+def vocode_ragged(voc, mels, ids, seed=0, max_rows=32, kernel='auto'):
+    """mels: list of float32 [T_b, 80] in [0, 1]; ids: global sentence index of each (keys the sampling noise).
+    Returns the list of float64 waves [(max(T_b, 21) - 1) * hop] in the order given."""
+    n = len(mels)
+    if n == 0:
+        return []
+    frames = [int(m.shape[0]) for m in mels]
+    waves = [None] * n
+    feat = mels[0].shape[1]
+    for chunk in plan_chunks(frames, max_rows):
+        T = max(max(frames[i] for i in chunk), MIN_FRAMES)
+        batch = np.zeros((len(chunk), feat, T), dtype=np.float32)      # zero frames past the end == the reference's own padding
+        uf = np.zeros(len(chunk), dtype=np.int32)
+        for r, i in enumerate(chunk):
+            batch[r, :, :frames[i]] = mels[i].T
+            uf[r] = max(frames[i], MIN_FRAMES)
+        out = voc.generate(torch.as_tensor(batch), seed=seed, utterance_ids=[int(ids[i]) for i in chunk], kernel=kernel,
+                           utt_frames=uf)
+        wave = out['wave'].cpu().numpy()
+        voc.check()
+        for r, i in enumerate(chunk):
+            waves[i] = wave[r, :(uf[r] - 1) * voc.hop].copy()
+    return waves
+
+
+def synthesize_batch(synth, wavernn_engine, texts, seed=0, utterance_offset=0, kernel='auto', max_rows=32):
+    """synth: tacotron.synthesizer.Synthesizer (loaded); wavernn_engine: engine.WaveRNNEngine; texts: pinyin strings.
+    Returns (list of float64 waves, list of mels [T_b, 80]) for sentences utterance_offset ... of a larger set."""
     mels, _ = synth.mels(texts, seed=seed, utterance_offset=utterance_offset)
-    keep = [m for m in mels]
-    T = max(max(m.shape[0] for m in keep), min_frames)
-    B = len(keep)
-    batch = np.zeros((B, keep[0].shape[1], T), dtype=np.float32)
-    frames = np.zeros(B, dtype=np.int32)
-    for b, m in enumerate(keep):
-        batch[b, :, :m.shape[0]] = m.T
-        frames[b] = max(m.shape[0], min_frames)     # shorter than the 20-hop fade-out cannot be faded (reference raises)
-    out = wavernn_engine.generate(torch.as_tensor(batch), seed=seed, utterance_offset=utterance_offset, kernel=kernel,
-                                  utt_frames=frames)
-    wave = out['wave'].cpu().numpy()
-    wavernn_engine.check()
+    ids = [utterance_offset + b for b in range(len(mels))]
+    return vocode_ragged(wavernn_engine, mels, ids, seed=seed, max_rows=max_rows, kernel=kernel), list(mels)
+
+
+def synthesize_sharded(synth, wavernn_engine, texts, seed=0, group=None, kernel='auto', max_rows=32):
+    """All ranks call this with the SAME `texts`; every rank returns all waves (input order) and all mels.
+    One process per GPU (`torch.distributed`); the only collective is the final all-gather of the padded waves."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mels, _ = synth.mels(texts, seed=seed, utterance_offset=0)           # replicated (see module docstring)
+    n = len(mels)
+    frames = [int(m.shape[0]) for m in mels]
+    mine = deal_round_robin(frames, world)[rank]
+    local = vocode_ragged(wavernn_engine, [mels[i] for i in mine], mine, seed=seed, max_rows=max_rows, kernel=kernel)
+    if world == 1:
+        out = [None] * n
+        for i, w in zip(mine, local):
+            out[i] = w
+        return out, list(mels)
     hop = wavernn_engine.hop
-    return [wave[b, :(frames[b] - 1) * hop].copy() for b in range(B)], keep
+    lens = [(max(f, MIN_FRAMES) - 1) * hop for f in frames]
+    per_rank = (n + world - 1) // world
+    nccl = dist.get_backend(group) == 'nccl'
+    dev = torch.device('cuda', torch.cuda.current_device()) if nccl else torch.device('cpu')
+    buf = torch.zeros((per_rank, max(lens) if lens else 1), dtype=torch.float64, device=dev)
+    for r, w in enumerate(local):
+        buf[r, :len(w)] = torch.as_tensor(w, device=dev)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    shares = deal_round_robin(frames, world)
+    out = [None] * n
+    for r, share in enumerate(shares):
+        host = parts[r].cpu().numpy()
+        for k, i in enumerate(share):
+            out[i] = host[k, :lens[i]].copy()
+    return out, list(mels)

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f'{name} declared in b200tts.h but not exported'
     assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
-    assert lib.b200tts_abi_version() == 1
+    assert lib.b200tts_abi_version() == 2
 
 
 def test_library_is_sm100a_and_has_no_cpu_path():

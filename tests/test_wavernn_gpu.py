@@ -400,3 +400,17 @@ def test_config2_single_utterance_5s_vs_oracle(torch_cuda):
     for i, s in enumerate(probe):
         assert np.abs(lg[i] - ref['logits'][s]).max() <= 5e-6 * scale + 1e-4, f'step {s}'
     np.testing.assert_allclose(out['wave'].cpu().numpy(), wo.finish_wave(lab, 1024, (T - 1) * 275, 275), rtol=0, atol=1e-12)
+
+
+def test_push_kernel_result_is_independent_of_batch_size(torch_cuda):
+    """The push kernel (B <= 32) sums the 128 block products of every output in one fixed order for all its row-count variants
+    (G = 4, 8, 16, 32), so a row's labels are BIT-IDENTICAL whatever batch it is generated in -- the property that makes an
+    N-rank sharded run reproduce the single-rank run exactly.  Full length (5775 steps), shipped checkpoint, Philox noise."""
+    eng, _ = engine_for('ckpt')
+    mels = synth.synth_mels(777, 20, 21)
+    full = eng.generate(mels, seed=5, kernel='grid')['labels'].cpu().numpy()              # 20 rows -> G = 32
+    for B in (1, 3, 7, 12):                                                                # G = 4, 4, 8, 16
+        part = eng.generate(mels[:B], seed=5, kernel='grid')['labels'].cpu().numpy()
+        assert np.array_equal(part, full[:B]), f'rows generated {B} at a time differ from the same rows in a batch of 20'
+    tail = eng.generate(mels[8:20], seed=5, utterance_offset=8, kernel='grid')['labels'].cpu().numpy()   # a "second rank's" shard
+    assert np.array_equal(tail, full[8:20])

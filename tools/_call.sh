@@ -1,22 +1,14 @@
 set -x
 mkdir -p gpurun_out
-( timeout 240 tools/exchange_bench.bin ) > gpurun_out/r02_exchange_bench.txt 2>&1
-cat gpurun_out/r02_exchange_bench.txt
-( timeout 600 python -m pytest tests/test_tacotron_gpu.py -q -x -k "teacher_forced" ) > gpurun_out/r02_c3_taco.log 2>&1
-tail -15 gpurun_out/r02_c3_taco.log
-python - <<'PY' > gpurun_out/r02_c3_e2e_diag.log 2>&1
-import time, sys, numpy as np, torch
-sys.path.insert(0, '.')
-from tacotronv2_wavernn_chinese_b200 import synth
-from tacotronv2_wavernn_chinese_b200.engine import WaveRNNEngine
-eng = WaveRNNEngine(synth.synth_state_dict(0), synth.DEFAULT_DIMS, device=0)
-m = synth.synth_mels(1, 256, 80)
-for i in range(5):
-    t0 = time.perf_counter(); r = eng.generate_host(m, seed=i); t1 = time.perf_counter()
-    print('generate_host', i, t1 - t0, 'kernel ms', eng.last_kernel_ms(), flush=True)
-md = torch.as_tensor(m).cuda()
-for i in range(3):
-    torch.cuda.synchronize(); t0 = time.perf_counter(); r = eng.generate(md, seed=i); torch.cuda.synchronize(); t1 = time.perf_counter()
-    print('generate dev', i, t1 - t0, flush=True)
-PY
-cat gpurun_out/r02_c3_e2e_diag.log
+( timeout 300 env B200TTS_GRID_PROF=1 python tools/quick_time.py grid 1,4,8,16,32 3000 ) > gpurun_out/r02_c4_push_time.log 2>&1
+tail -12 gpurun_out/r02_c4_push_time.log
+( timeout 300 env B200TTS_PUSH_MIN_G=8 python tools/quick_time.py grid 1,4 3000 ) > gpurun_out/r02_c4_push_time_g8.log 2>&1
+tail -3 gpurun_out/r02_c4_push_time_g8.log
+( timeout 600 python -m pytest tests/test_wavernn_gpu.py -q -x -k "mapping and not 256 and not 300 and not 128 and not 100 and not 64 or fold or philox or invariance or golden or independent" ) > gpurun_out/r02_c4_tests.log 2>&1
+tail -8 gpurun_out/r02_c4_tests.log
+( timeout 600 python -m pytest tests/test_tacotron_gpu.py -q -x -k "pipeline" ) > gpurun_out/r02_c4_tests2.log 2>&1
+tail -8 gpurun_out/r02_c4_tests2.log
+( timeout 900 python bench.py --workload text2audio --steps 1 --warmup 1 ) > gpurun_out/r02_c4_t2a_n1.json 2> gpurun_out/r02_c4_t2a_n1.err
+cat gpurun_out/r02_c4_t2a_n1.json; tail -5 gpurun_out/r02_c4_t2a_n1.err
+( timeout 300 python bench.py --workload tacotron --steps 3 --warmup 2 ) > gpurun_out/r02_c4_taco.json 2> gpurun_out/r02_c4_taco.err
+cat gpurun_out/r02_c4_taco.json; tail -5 gpurun_out/r02_c4_taco.err
