@@ -16,6 +16,7 @@
 #include "wavernn_utt.cuh"
 #include "wavernn_grid.cuh"
 #include "wavernn_push.cuh"
+#include "wavernn_pushmg.cuh"
 #include "taco_decoder.cuh"
 #include "taco_encpost.cuh"
 
@@ -761,8 +762,10 @@ static void launch_push_t(b200tts_wavernn* ctx, PushArgs& a, cudaStream_t st) {
   ctx->launches++;
 }
 
+// rows per group of the push kernels.  Measured (profiles/r02_push_v3_phase_cycles.txt): 8 rows 9.2 us per step, 4 rows 14.5 us
+// (64 hot L2 lines polled by 65 536 threads) -- so up to 8 rows run the 8-row variant; env B200TTS_PUSH_MIN_G is an A/B switch.
 static inline int push_rows(int B) {
-  static const int min_g = getenv("B200TTS_PUSH_MIN_G") ? atoi(getenv("B200TTS_PUSH_MIN_G")) : 4;   // A/B switch (timing only)
+  static const int min_g = getenv("B200TTS_PUSH_MIN_G") ? atoi(getenv("B200TTS_PUSH_MIN_G")) : 8;
   const int g = B <= 4 ? 4 : (B <= 8 ? 8 : (B <= 16 ? 16 : 32));
   return g < min_g ? (min_g <= 8 ? 8 : (min_g <= 16 ? 16 : 32)) : g;
 }
@@ -770,7 +773,10 @@ static inline int push_rows(int B) {
 // Can this call take the push kernel?  (env B200TTS_PUSH=0 keeps the round-1 mappings for A/B timing.)
 static bool push_eligible(const b200tts_wavernn* ctx, int rows) {
   static const bool off = getenv("B200TTS_PUSH") != nullptr && getenv("B200TTS_PUSH")[0] == '0';
-  return ctx->pm.ok && ctx->gm.ok && rows <= 32 && !off;
+  // Default 32: the multi-group form (wavernn_pushmg.cuh, 33 ... 256 rows) is parity-green but MEASURED SLOWER than the round-1 wide
+  // mapping (144 vs 68 us per lock-step at 256 rows, profiles/r02_pushmg_time.txt), so it only runs when asked for.
+  static const int max_rows = getenv("B200TTS_PUSH_MAX_ROWS") ? atoi(getenv("B200TTS_PUSH_MAX_ROWS")) : kMgG;
+  return ctx->pm.ok && ctx->gm.ok && rows <= max_rows && rows <= kMgG * kMgMaxGroups && !off;
 }
 
 // `fold` != null: rows are the folds of ONE source utterance of T0 frames (conditioning tables of utterance 0, row u
@@ -778,9 +784,11 @@ static bool push_eligible(const b200tts_wavernn* ctx, int rows) {
 static void launch_push(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cudaStream_t st, const FoldGeom* fold, int T0) {
   const b200tts_wavernn_cfg& c = ctx->cfg;
   const PushModel& pm = ctx->pm;
-  const int rows = ua.B, G = push_rows(rows);
+  const int rows = ua.B;
+  const int ng = rows > kMgG ? (rows + kMgG - 1) / kMgG : 1;          // > 32 rows: multi-group kernel, groups of 32
+  const int G = ng > 1 ? kMgG : push_rows(rows);
   const int T = fold ? T0 : ua.T, hop = c.hop_length;
-  const int tab_rows = fold ? 1 : G, src_rows = fold ? 1 : rows;
+  const int tab_rows = fold ? 1 : ng * G, src_rows = fold ? 1 : rows;
   // conditioning tables [tab_rows][T+1][ncta][52]
   ctx->push_tab.ensure((size_t)tab_rows * (T + 1) * pm.ncta * kPushCondRows * sizeof(float));
   {
@@ -791,7 +799,7 @@ static void launch_push(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
     B200_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  const size_t nvec = (size_t)kPushVecs * 2 * pm.ncta * G * 4, nbest = (size_t)pm.ncta * G;
+  const size_t nvec = (size_t)ng * kPushVecs * 2 * pm.ncta * G * 4, nbest = (size_t)ng * pm.ncta * G;
   ctx->push_vec.ensure(nvec * sizeof(float));
   ctx->push_best.ensure(nbest * sizeof(unsigned long long) + 64);
   int* d_err = reinterpret_cast<int*>(ctx->push_best.as<unsigned long long>() + nbest);
@@ -808,6 +816,7 @@ static void launch_push(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   a.fir = ctx->d_fir;
   a.NT = ctx->NT;
   a.B = rows; a.S = ua.S; a.T = T; a.hop = hop; a.steps = ua.steps;
+  a.ng = ng;
   a.row_stride = fold ? fold->stride : 0;
   a.S_src = T * hop;
   a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.utt_ids = ua.utt_ids; a.q = ua.q;
@@ -821,7 +830,19 @@ static void launch_push(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
     ctx->last_grid_ncta = 0;
   }
   B200_CUDA(cudaEventRecord(ctx->ev0, st));
-  switch (G) {
+  if (ng > 1) {
+    const MgLayout L(ng);
+    size_t smem = ((size_t)pm.blob + (size_t)L.total) * sizeof(float);
+    REQUIRE(smem + 2048 <= 227 * 1024, B200TTS_EINVAL, "multi-group push kernel: shared memory budget exceeded");
+    B200_CUDA(cudaFuncSetAttribute(wavernn_pushmg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wavernn_pushmg_kernel, kPushThreads, smem));
+    REQUIRE(per_sm * ctx->sm_count >= pm.ncta, B200TTS_EINVAL, "multi-group push kernel cannot be made co-resident on this device");
+    PushModel m = pm;
+    void* args[] = {(void*)&m, (void*)&a};
+    B200_CUDA(cudaLaunchCooperativeKernel((const void*)wavernn_pushmg_kernel, dim3(pm.ncta), dim3(kPushThreads), args, smem, st));
+    ctx->launches++;
+  } else switch (G) {
     case 4: launch_push_t<4>(ctx, a, st); break;
     case 8: launch_push_t<8>(ctx, a, st); break;
     case 16: launch_push_t<16>(ctx, a, st); break;

@@ -66,6 +66,7 @@ struct PushArgs {
   const float* fir;              // [hop][NT] composite polyphase FIR of the upsampling network
   int NT;
   int B, S, T, hop, steps;
+  int ng;                        // multi-group kernel (wavernn_pushmg.cuh): groups of 32 rows; vec is [ng][6][2][ncta][32][4], best [ng][ncta][32]
   int row_stride;                // 0: row u is utterance u.  > 0 (fold-with-overlap): row u = samples [u*row_stride, ...) of utterance 0
   int S_src;                     // samples of the source utterance (conditioning is ZERO beyond, fatchord_version.py:315-317)
   int rng_mode;
