@@ -1,8 +1,9 @@
 """N-rank sharded generation == single-rank generation, BIT FOR BIT, on the real kernels.
 
 The property rests on two things the kernels guarantee: the sampling noise is keyed by the GLOBAL utterance index, and the push
-kernels (<= 32 rows per group, single- and multi-group) add the 128 block products of every output in one fixed order whatever
-the row count, so a row's arithmetic does not depend on the batch it sits in.
+kernels (<= 32 rows per launch) add the 128 block products of every output in one fixed order whatever the row count, so a row's
+arithmetic does not depend on the batch it sits in.  (Above 32 rows per GPU the wide mapping of wavernn_grid.cuh runs, whose
+summation order depends on its tile shape: there a shard reproduces the single-rank rows up to sampling near-ties only.)
   * test_shards_equal_single_rank_one_gpu: the shards of 2-, 4- and 8-rank runs computed one after the other on ONE GPU through
     dist.shard_bounds + the same engine call dist.generate_sharded makes (runs everywhere, incl. the driver's 1-GPU box);
   * test_generate_sharded_nccl_world2: the real thing over NCCL with one process per GPU (skipped with fewer than 2 GPUs)."""
@@ -26,7 +27,7 @@ def _engine():
     return WaveRNNEngine(sd, synth.DEFAULT_DIMS)
 
 
-@pytest.mark.parametrize('n', [24, 64])
+@pytest.mark.parametrize('n', [24, 32])      # <= 32 rows in total: every shard AND the single-rank run take the push kernels
 def test_shards_equal_single_rank_one_gpu(n):
     import torch
     if not torch.cuda.is_available():

@@ -115,6 +115,96 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(const uint16_t* __restrict
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+
+// ---- round-2 experiment: K-CHUNKED accumulation.  The tensor core's fp32 accumulator truncates on every
+// MMA, and over the 32 k-steps of K = 512 that bias is what makes the 6-product result 7x less accurate than an fp32 FMA loop.
+// Here the dominant hi x hi product is accumulated in TMEM only over CH consecutive k-steps (K = 16*CH) per accumulator; the
+// 32/CH chunk accumulators and the one accumulator of the five small products are added in fp32 registers (round to nearest).
+template <int CH>
+__global__ void __launch_bounds__(128, 1) umma_chunk_kernel(const uint16_t* __restrict__ gA, const uint16_t* __restrict__ gB,
+                                                            float* __restrict__ D, int reps, int* status) {
+  constexpr int NCHUNK = 32 / CH;                      // reps * KS = 32 k-steps in total
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint16_t* sA = reinterpret_cast<uint16_t*>(smem);
+  uint16_t* sB = sA + A_ELEMS;
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < A_ELEMS / 8; i += blockDim.x) reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(gA)[i];
+  for (int i = tid; i < B_ELEMS / 8; i += blockDim.x) reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(gB)[i];
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  if (tid == 0) {
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    const uint64_t dA0 = make_desc(a0, (M / 8) * 128, 128), dB0 = make_desc(b0, (N / 8) * 128, 128);
+    bool small_started = false;
+    for (int r = 0; r < reps; ++r)
+      for (int s = 0; s < KS; ++s) {
+        const int kstep = r * KS + s;
+        for (int q = 0; q < 6; ++q) {
+          const int kPi[6] = {2, 1, 0, 1, 0, 0}, kPj[6] = {0, 1, 2, 0, 1, 0};
+          const uint64_t da = dA0 + (uint64_t)((2u * ((kPi[q] * KS + s) * A_TILE)) >> 4);
+          const uint64_t db = dB0 + (uint64_t)((2u * ((kPj[q] * KS + s) * B_TILE)) >> 4);
+          uint32_t slot, acc;
+          if (q == 5) { slot = (uint32_t)(kstep / CH); acc = (kstep % CH) ? 1u : 0u; }           // hi x hi: one accumulator per chunk
+          else { slot = (uint32_t)NCHUNK; acc = small_started ? 1u : 0u; small_started = true; }   // the five small products: one accumulator
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem + slot * N),
+              "l"(da), "l"(db), "r"(idesc), "r"(acc));
+        }
+      }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+  }
+  {
+    uint32_t done = 0;
+    long long ts = clock64();
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
+      if (!done && clock64() - ts > 2000000000LL) { if (tid == 0) *status = 1; break; }
+    }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  float sum[16], chunk[NCHUNK][16];
+  for (int j = 0; j <= NCHUNK; ++j) {
+    uint32_t v[16];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * N);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int c = 0; c < 16; ++c) {
+      if (j < NCHUNK) chunk[j][c] = __uint_as_float(v[c]);
+      else sum[c] = __uint_as_float(v[c]);
+    }
+  }
+  // pairwise tree over the chunk accumulators, then the small-product accumulator
+  for (int c = 0; c < 16; ++c) {
+    for (int w = 1; w < NCHUNK; w <<= 1)
+      for (int j = 0; j + w < NCHUNK; j += 2 * w) chunk[j][c] = __fadd_rn(chunk[j][c], chunk[j + w][c]);
+    sum[c] = __fadd_rn(chunk[0][c], sum[c]);
+  }
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < 16; ++c) D[row * N + c] = sum[c];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 static uint16_t bf16_rne(float f) {
   uint32_t u; memcpy(&u, &f, 4);
   u += 0x7FFFu + ((u >> 16) & 1u);
@@ -190,6 +280,41 @@ int main() {
   printf("  tcgen05 bf16 x bf16 (1 product) : %.3e\n", maxerr(out));
   run(reps, 6, 1, out, cyc);
   printf("  tcgen05 bf16x3, 6 products      : %.3e   (%d MMAs in %.0f cycles)\n", maxerr(out), reps * KS * 6, cyc);
+  {
+    auto run_chunk = [&](int ch) {
+      cudaMemset(dS, 0, 4);
+      if (ch == 4) { cudaFuncSetAttribute(umma_chunk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_chunk_kernel<4><<<1, 128, smem>>>(dA, dB, dD, reps, dS); }
+      else if (ch == 2) { cudaFuncSetAttribute(umma_chunk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_chunk_kernel<2><<<1, 128, smem>>>(dA, dB, dD, reps, dS); }
+      else { cudaFuncSetAttribute(umma_chunk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_chunk_kernel<8><<<1, 128, smem>>>(dA, dB, dD, reps, dS); }
+      cudaError_t e = cudaDeviceSynchronize();
+      int st = 0; cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess || st) { printf("chunk kernel failed: %s status=%d\n", cudaGetErrorString(e), st); exit(1); }
+      out.resize(M * N); cudaMemcpy(out.data(), dD, sizeof(float) * M * N, cudaMemcpyDeviceToHost);
+      return maxerr(out);
+    };
+    // CPU models of the same split arithmetic with IEEE accumulation, to separate splitting error from accumulator truncation
+    {
+      std::vector<float> m(M * N);
+      for (int r = 0; r < M; ++r)
+        for (int c = 0; c < N; ++c) {
+          float acc = 0.f;
+          for (int rep = 0; rep < reps; ++rep)
+            for (int k = 0; k < K; ++k) {
+              float a = A[r * K + k], b = B[c * K + k], ap[3], bp[3];
+              for (int p = 0; p < 3; ++p) { ap[p] = bf16_to_f(bf16_rne(a)); a -= ap[p]; bp[p] = bf16_to_f(bf16_rne(b)); b -= bp[p]; }
+              double t = 0;
+              for (int i = 0; i < 3; ++i) for (int j = 0; i + j <= 2; ++j) t += (double)ap[i] * bp[j];
+              acc = (float)((double)acc + t);
+            }
+          m[r * N + c] = acc;
+        }
+      printf("  CPU model: 6 products, fp32 round-to-nearest accumulation over k : %.3e\n", maxerr(m));
+    }
+    printf("  tcgen05 bf16x3, hi x hi in chunks of K=128 (8 k-steps per accumulator, 4 accumulators) + registers : %.3e\n", run_chunk(8));
+    printf("  tcgen05 bf16x3, hi x hi in chunks of K= 64 (4 k-steps per accumulator, 8 accumulators) + registers : %.3e\n", run_chunk(4));
+    printf("  tcgen05 bf16x3, hi x hi in chunks of K= 32 (2 k-steps per accumulator, 16 accumulators) + registers: %.3e\n", run_chunk(2));
+    printf("  (kill criterion of VERDICT r1 next #8: <= 6e-7 of max|out|)\n");
+  }
   for (int blocks : {1, 128}) {
     const int r = 256;
     const double n = (double)r * KS * 6;
