@@ -19,6 +19,7 @@
 #include "wavernn_pushmg.cuh"
 #include "taco_decoder.cuh"
 #include "taco_encpost.cuh"
+#include "taco_grid.cuh"
 
 using namespace b200tts;
 
@@ -1152,6 +1153,11 @@ struct b200tts_taco {
   const float *post_pk = nullptr, *post_pb = nullptr;
   int post_channels = 0;
   int64_t launches = 0;
+  // weight-stationary single-sentence decoder (taco_grid.cuh)
+  TacoGridModel tgm{};
+  DeviceBuf tg_blob, tg_vec;
+  bool tg_ok = false;
+  int sm_count = 0;
 };
 
 extern "C" int b200tts_taco_create(b200tts_taco** out, int device, const b200tts_taco_cfg* cfg, const b200tts_tensor* weights,
@@ -1269,6 +1275,87 @@ extern "C" int b200tts_taco_create(b200tts_taco** out, int device, const b200tts
     for (int i = 0; i < 5; ++i) ctx->post_conv[i] = bind(postc[i]);
     ctx->post_pk = b + o_pk; ctx->post_pb = b + o_pb;
   }
+  // ---- per-block weight blobs of the weight-stationary single-sentence decoder (taco_grid.cuh) ----
+  {
+    int coop = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    B200_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (coop && ctx->sm_count >= kTgCtas && P == 256 && U == 256 && E == 512 && AD == 128 && M <= 96 && KW <= 64) {
+      TacoGridModel& g = ctx->tgm;
+      g.M = M; g.P = P; g.U = U; g.E = E; g.KW = KW;
+      int off = 0;
+      auto take = [&](int n) { int o0 = off; off += (n + 3) & ~3; return o0; };
+      g.oW1 = take(M * 2); g.oB1 = take(2);
+      g.oWfold = take((U + E) * 2); g.oBfold = take(2);
+      g.oW2 = take(P * 2); g.oB2 = take(2);
+      g.oK1 = take((P + E + U) * 8); g.oBk1 = take(8);
+      g.oK2 = take(2 * U * 8); g.oBk2 = take(8);
+      g.oWq = take(U);
+      g.oFloc = take(KW + 4);
+      g.oProj = take((U + E) * 4 + 4);
+      g.blob = off;
+      const float* H = pk.h.data();
+      const float *W1 = H + o[0], *b1 = H + o[1], *W2 = H + o[2], *b2 = H + o[3], *K1 = H + o[4], *bk1 = H + o[5], *K2 = H + o[6],
+                  *bk2 = H + o[7], *Wq = H + o[8], *lock = H + o[9], *locb = H + o[10], *locl = H + o[11], *va = H + o[12], *ba = H + o[13],
+                  *muk = H + o[14], *mub = H + o[15], *frk = H + o[16], *frb = H + o[17], *stk = H + o[18], *stb = H + o[19];
+      // W_f . W_1 and b_f . W_1 + b_1 in float64
+      std::vector<double> fold((size_t)(U + E) * P), bfold(P);
+      for (int i = 0; i < U + E; ++i)
+        for (int p2 = 0; p2 < P; ++p2) {
+          double a = 0;
+          for (int m = 0; m < M; ++m) a += (double)frk[(size_t)i * M + m] * (double)W1[(size_t)m * P + p2];
+          fold[(size_t)i * P + p2] = a;
+        }
+      for (int p2 = 0; p2 < P; ++p2) {
+        double a = b1[p2];
+        for (int m = 0; m < M; ++m) a += (double)frb[m] * (double)W1[(size_t)m * P + p2];
+        bfold[p2] = a;
+      }
+      std::vector<float> hb((size_t)kTgCtas * g.blob, 0.f);
+      for (int c2 = 0; c2 < kTgCtas; ++c2) {
+        float* d = &hb[(size_t)c2 * g.blob];
+        for (int j = 0; j < 2; ++j) {
+          const int col = 2 * c2 + j;
+          for (int m = 0; m < M; ++m) d[g.oW1 + m * 2 + j] = W1[(size_t)m * P + col];
+          d[g.oB1 + j] = b1[col];
+          for (int i = 0; i < U + E; ++i) d[g.oWfold + i * 2 + j] = (float)fold[(size_t)i * P + col];
+          d[g.oBfold + j] = (float)bfold[col];
+          for (int k = 0; k < P; ++k) d[g.oW2 + k * 2 + j] = W2[(size_t)k * P + col];
+          d[g.oB2 + j] = b2[col];
+          for (int gate = 0; gate < 4; ++gate) {
+            const int src = gate * U + col, dst = gate * 2 + j;
+            for (int k = 0; k < P + E + U; ++k) d[g.oK1 + k * 8 + dst] = K1[(size_t)k * 4 * U + src];
+            d[g.oBk1 + dst] = bk1[src];
+            for (int k = 0; k < 2 * U; ++k) d[g.oK2 + k * 8 + dst] = K2[(size_t)k * 4 * U + src];
+            d[g.oBk2 + dst] = bk2[src];
+          }
+        }
+        for (int u = 0; u < U; ++u) d[g.oWq + u] = Wq[(size_t)u * AD + c2];
+        double bl = ba[c2];
+        for (int f = 0; f < NF; ++f) bl += (double)locb[f] * (double)locl[(size_t)f * AD + c2];
+        for (int k = 0; k < KW; ++k) {
+          double a = 0;
+          for (int f = 0; f < NF; ++f) a += (double)lock[(size_t)k * NF + f] * (double)locl[(size_t)f * AD + c2];
+          d[g.oFloc + k] = (float)a;
+        }
+        d[g.oFloc + KW] = (float)bl;
+        d[g.oFloc + KW + 1] = va[c2];
+        d[g.oFloc + KW + 2] = 1.0f - c.zoneout;
+        d[g.oFloc + KW + 3] = c.zoneout;
+        for (int i = 0; i < U + E; ++i) {
+          d[g.oProj + i * 4 + 0] = muk[i < U ? E + i : i - U];          // attention.py:229 concatenates [context, query]
+          d[g.oProj + i * 4 + 1] = stk[i];
+          d[g.oProj + i * 4 + 2] = c2 < M ? frk[(size_t)i * M + c2] : 0.f;
+        }
+        d[g.oProj + (U + E) * 4 + 0] = mub[0];
+        d[g.oProj + (U + E) * 4 + 1] = stb[0];
+        d[g.oProj + (U + E) * 4 + 2] = c2 < M ? frb[c2] : 0.f;
+      }
+      ctx->tg_blob.ensure(hb.size() * sizeof(float));
+      B200_CUDA(cudaMemcpy(ctx->tg_blob.p, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+      ctx->tg_ok = true;
+    }
+  }
   cleanup.c = nullptr;
   *out = ctx;
   API_END
@@ -1283,6 +1370,8 @@ extern "C" void b200tts_taco_destroy(b200tts_taco* ctx) {
   ctx->keys.release();
   ctx->act_a.release();
   ctx->act_b.release();
+  ctx->tg_blob.release();
+  ctx->tg_vec.release();
   if (prev >= 0) cudaSetDevice(prev);
   delete ctx;
 }
@@ -1309,6 +1398,40 @@ static int taco_decode_impl(b200tts_taco* ctx, const float* d_memory, const int3
   a.rng_mode = d.mode; a.seed = d.seed; a.utt_offset = d.utterance_offset; a.masks = d.d_masks;
   a.frames = d_frames; a.stop = d_stop; a.align = d_align; a.nsteps = d_nsteps;
   a.forced = d_forced;
+  static const bool tg_off = getenv("B200TTS_TACO_GRID") != nullptr && getenv("B200TTS_TACO_GRID")[0] == '0';
+  if (B == 1 && ctx->tg_ok && !tg_off) {
+    // ONE sentence: the weight-stationary 128-block decoder (taco_grid.cuh).  The sentence length is needed on the host to size
+    // the exchange buffers; d_lengths is a device pointer, so Tx_max (the caller's padded length) bounds it and the kernel
+    // reads the true length itself.
+    const TacoGridModel& g = ctx->tgm;
+    const int Txp = (Tx_max + 3) & ~3;
+    const size_t copy = (size_t)2048 + (size_t)kTgCtas * Txp;
+    ctx->tg_vec.ensure(2 * copy * sizeof(float) + 64);
+    int* d_err = reinterpret_cast<int*>(ctx->tg_vec.as<float>() + 2 * copy);
+    push_init_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->tg_vec.as<uint32_t>(), 2 * copy, nullptr, 0, d_err);
+    B200_CUDA(cudaGetLastError());
+    TacoGridArgs ga{};
+    ga.wblob = ctx->tg_blob.as<float>();
+    ga.vec = ctx->tg_vec.as<float>();
+    ga.error = d_err;
+    ga.memory = d_memory; ga.keys = ctx->keys.as<float>();
+    ga.lengths = d_lengths;
+    ga.Tx = Tx_max; ga.Txp = Txp; ga.max_steps = max_steps; ga.window = window;
+    ga.rng_mode = d.mode; ga.seed = d.seed; ga.utt = d.utterance_offset; ga.masks = d.d_masks;
+    ga.forced = d_forced; ga.Tx_alloc = Tx_max;
+    ga.frames = d_frames; ga.stop = d_stop; ga.align = d_align; ga.nsteps = d_nsteps;
+    const size_t fl = (size_t)g.blob + (size_t)(w.P + w.E + w.U) + 2 * w.U + (w.U + w.E) + w.P + 128 + 24 * (size_t)Txp + 176;
+    const size_t smem = fl * sizeof(float);
+    REQUIRE(smem <= 227 * 1024, B200TTS_EINVAL, "taco_grid_kernel: shared memory budget exceeded");
+    B200_CUDA(cudaFuncSetAttribute(taco_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TacoGridModel gm = g;
+    void* args[] = {(void*)&gm, (void*)&ga};
+    B200_CUDA(cudaLaunchCooperativeKernel((const void*)taco_grid_kernel, dim3(kTgCtas), dim3(kTgThreads), args, smem, st));
+    taco_grid_finish_kernel<<<1, 1, 0, st>>>(d_err, d_nsteps);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 4;
+    return B200TTS_OK;
+  }
   size_t fl = 128 + w.P + (w.P + w.E + w.U) + 2 * w.U + 4 * w.U + 2 * w.U + (w.U + w.E) + w.A + 3 * kTacoMaxTx + 96 + 64 +
               (size_t)w.KW * w.NF + (size_t)w.NF * w.A + 16384;
   size_t smem = fl * sizeof(float);

@@ -196,6 +196,8 @@ __device__ __forceinline__ void push_gemm(const float* __restrict__ W /*[ROWS][5
     for (int j = 0; j < UT; ++j) off[i * UT + j] = ((kq * NKB + i) * G + ul + NU * j) * 4;
   float4 a[NL];
   poll_entries<NL>(vecbase, off, a, pg);
+  // (settling and multiplying block by block, so that the FMAs of block i overlap the loads of block i+1, was measured
+  //  SLOWER: 19.4 vs 14.4 us per step at 16 rows, 24.9 vs 21.7 at 32 -- the per-block leaves no longer fit the register file)
   float acc[ROWS][UT];
   const float4* W4 = reinterpret_cast<const float4*>(W);
 #pragma unroll
@@ -249,15 +251,17 @@ __device__ __forceinline__ float push_part_sum(const float* part, int r, int u) 
   return v;
 }
 
-// conditioning of step `t` for all rows -> cdst[36][G]  (rows 0-15: I rows 0-3 and folded GRU-1 rows, FIR-combined mel
-// projections + aux projection + bias; rows 16-27 GRU-2, 28-31 fc1, 32-35 fc2: aux projection + bias).
-// All (<= 1 + kMaxTaps) table loads of an item are issued before the first FMA: one L2 round trip per item.
+// Conditioning of step `t`.  Rows 0-15 (I rows 0-3 and the folded GRU-1 rows: FIR-combined mel projections + aux projection
+// + bias) change every sample -> push_cond16, one (row, cond row) item per thread at 32 rows, all (<= 1 + kMaxTaps) table
+// loads of an item in flight at once.  Rows 16-35 (GRU-2 12, fc1 4, fc2 4: aux projection + bias) are constant within a
+// frame -> push_cond20, refreshed only when the next step starts a new frame (every step in fold mode, where rows sit at
+// different phases).
 template <int G>
-__device__ __forceinline__ void push_cond(const PushArgs& A, const float* fir_s, float* cdst, int c, int ncta, int t, int tid) {
+__device__ __forceinline__ void push_cond16(const PushArgs& A, const float* fir_s, float* cdst, int c, int ncta, int t, int tid) {
   const size_t fstride = (size_t)ncta * kPushCondRows;
   const int fr0 = t / A.hop, ph0 = t - fr0 * A.hop;                   // row_stride == 0: every row is at the same frame / phase
-  for (int it = tid; it < 36 * G; it += kPushThreads) {
-    const int u = it / 36, r = it - u * 36;
+  for (int it = tid; it < 16 * G; it += kPushThreads) {
+    const int u = it >> 4, r = it & 15;
     int src = u, fr = fr0, ph = ph0;
     bool beyond = false;
     if (A.row_stride) {
@@ -269,18 +273,30 @@ __device__ __forceinline__ void push_cond(const PushArgs& A, const float* fir_s,
     }
     const float* row = A.tab + (((size_t)src * (A.T + 1) + fr) * ncta + c) * kPushCondRows;
     float v = __ldg(row + 16 + r);
-    if (r < 16 && !beyond) {
-      float pm[kMaxTaps];
+    float pm[kMaxTaps];
 #pragma unroll
-      for (int j = 0; j < kMaxTaps; ++j) {
-        const int f = fr + j - A.NT / 2;
-        pm[j] = (j < A.NT && f >= 0 && f < A.T) ? __ldg(row + ((ptrdiff_t)(f - fr)) * (ptrdiff_t)fstride + r) : 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < kMaxTaps; ++j)
-        if (j < A.NT) v = fmaf(fir_s[ph * A.NT + j], pm[j], v);        // an absent frame contributes fir * 0 = 0 exactly
+    for (int j = 0; j < kMaxTaps; ++j) {
+      const int f = fr + j - A.NT / 2;
+      pm[j] = (!beyond && j < A.NT && f >= 0 && f < A.T) ? __ldg(row + ((ptrdiff_t)(f - fr)) * (ptrdiff_t)fstride + r) : 0.f;
     }
+#pragma unroll
+    for (int j = 0; j < kMaxTaps; ++j)
+      if (j < A.NT) v = fmaf(fir_s[ph * A.NT + j], pm[j], v);          // an absent frame contributes fir * 0 = 0 exactly
     cdst[r * G + u] = v;
+  }
+}
+template <int G>
+__device__ __forceinline__ void push_cond20(const PushArgs& A, float* cdst, int c, int ncta, int t, int tid) {
+  const int fr0 = t / A.hop;
+  for (int it = tid; it < 20 * G; it += kPushThreads) {
+    const int u = it / 20, r = it - u * 20;
+    int src = u, fr = fr0;
+    if (A.row_stride) {
+      const long long n = (long long)u * A.row_stride + t;
+      src = 0;
+      fr = n >= A.S_src ? A.T : (int)(n / A.hop);
+    }
+    cdst[r * G + u] = __ldg(A.tab + (((size_t)src * (A.T + 1) + fr) * ncta + c) * kPushCondRows + 32 + r);
   }
 }
 
@@ -326,7 +342,10 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
   for (int i = tid; i < A.hop * A.NT; i += kPushThreads) fir_s[i] = A.fir[i];
   for (int i = tid; i < 12 * G; i += kPushThreads) { gh1[i] = 0.f; gh2[i] = 0.f; }     // W_hh . 0  (h1 = h2 = 0, :194-195)
   __syncthreads();
-  push_cond<G>(A, fir_s, cond, c, ncta, 0, tid);
+  float* cond16 = cond;                       // [2][16][G]  rows 0-15 of step t (parity buffers, written one step ahead)
+  float* cond20 = cond + 2 * 16 * G;          // [20][G]     rows 16-35 of the current frame
+  push_cond16<G>(A, fir_s, cond16, c, ncta, 0, tid);
+  push_cond20<G>(A, cond20, c, ncta, 0, tid);
   __syncthreads();
 
   PollGuard pg{A.error, 0, 0, false};
@@ -393,7 +412,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
     }
     if (t == A.steps) break;                                // the extra trip only collects the last winner
     if (gate) {
-      const float* cd = cond + par * 36 * G;
+      const float* cd = cond16 + par * 16 * G;
       const float* wAx = Wb + M.oAx;
       const float* bhh = Wb + M.obhh1;
       const float iout = fmaf(wAx[gj], x, cd[gj * G + gu]);
@@ -416,7 +435,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
     PUSH_MARK(2);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (gate) {
-      const float* cd = cond + par * 36 * G + 16 * G;
+      const float* cd = cond20;
       const float* bhh = Wb + M.obhh2;
       const float h = gru_update(push_part_sum<G, 12>(partX, gj, gu) + cd[gj * G + gu],
                                  push_part_sum<G, 12>(partX, 4 + gj, gu) + cd[(4 + gj) * G + gu],
@@ -440,7 +459,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
     PUSH_MARK(5);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (gate) {
-      const float v = push_part_sum<G, 4>(partX, gj, gu) + cond[par * 36 * G + (28 + gj) * G + gu];
+      const float v = push_part_sum<G, 4>(partX, gj, gu) + cond20[(12 + gj) * G + gu];
       st_relaxed_f32(vecp(PV_F1, par) + ((size_t)c * G + gu) * 4 + gj, fmaxf(v, 0.f));
     }
     __syncwarp();
@@ -452,10 +471,12 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
 
     // ================= P4: fc2 + relu on f1(t) =================
     push_gemm<G, 4>(Wb + M.ofc2, vecp(PV_F1, par), partX, ul, kq, warp, lane, pg);
+    // the fc2 conditioning value is taken BEFORE the barrier: after it the other threads may refresh cond20 for the next frame
+    const float cv4 = gate ? cond20[(16 + gj) * G + gu] : 0.f;
     PUSH_MARK(7);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (gate) {
-      const float v = push_part_sum<G, 4>(partX, gj, gu) + cond[par * 36 * G + (32 + gj) * G + gu];
+      const float v = push_part_sum<G, 4>(partX, gj, gu) + cv4;
       const size_t e = ((size_t)c * G + gu) * 4 + gj;
       st_relaxed_f32(vecp(PV_F2, par) + e, fmaxf(v, 0.f));
       // REARM (shadow of the f2 exchange).  Every CTA's winner of step t-1 was seen at the top of this step, and a CTA
@@ -468,9 +489,11 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncwarp();
-    // shadow: conditioning of step t+1 into the other cond buffer (this step's rows 0-31 are consumed; rows 32-35 of
-    // cond[par] were read by the gate threads just above)
-    if (t + 1 < A.steps) push_cond<G>(A, fir_s, cond + (par ^ 1) * 36 * G, c, ncta, t + 1, tid);
+    // shadow: conditioning of step t+1 (rows 0-15 into the other parity buffer; rows 16-35 only when a new frame starts)
+    if (t + 1 < A.steps) {
+      push_cond16<G>(A, fir_s, cond16 + (par ^ 1) * 16 * G, c, ncta, t + 1, tid);
+      if (A.row_stride || (t + 1) % A.hop == 0) push_cond20<G>(A, cond20, c, ncta, t + 1, tid);
+    }
     PUSH_MARK(8);
 
     // ================= P5: fc3 on f2(t) + Gumbel-max over this CTA's 8 classes =================

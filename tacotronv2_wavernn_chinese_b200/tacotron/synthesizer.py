@@ -62,6 +62,8 @@ class Synthesizer:
         dec = eng.decode(mem, lengths, seed=seed, utterance_offset=utterance_offset, max_steps=ms, window=window, want_align=True)
         mel = eng.postnet(dec['frames'], dec['nsteps'])
         n = dec['nsteps'].cpu().numpy()
+        if (n < 0).any():
+            raise RuntimeError('Tacotron decoder kernel gave up waiting for a peer thread block (nsteps < 0); results are invalid')
         stop = dec['stop'].cpu().numpy()
         mel_h = mel.cpu().numpy()
         out = []

@@ -52,7 +52,7 @@ def test_struct_layouts_match_header():
     _, L = _lib()
     assert ctypes.sizeof(L.WaveRNNCfg) == 14 * 4
     assert ctypes.sizeof(L.Tensor) == 8 + 8 + 8 + 32
-    assert ctypes.sizeof(L.Rng) == 32
+    assert ctypes.sizeof(L.Rng) == 40          # ABI 2: + d_utterance_ids
     assert ctypes.sizeof(L.GenOpts) == 48
 
 

@@ -1,13 +1,8 @@
 set -x
 mkdir -p gpurun_out
-( timeout 120 tools/umma_split_bench.bin ) > gpurun_out/r02_umma_chunk.txt 2>&1
-head -12 gpurun_out/r02_umma_chunk.txt
-( timeout 1500 python -m pytest tests -m gpu -q --durations=8 ) > gpurun_out/r02_c7_gputests.log 2>&1
-tail -25 gpurun_out/r02_c7_gputests.log
-( timeout 900 python bench.py --steps 4 --warmup 3 ) > gpurun_out/r02_c7_bench.json 2> gpurun_out/r02_c7_bench.err
-python -c "
-import json
-d=json.loads(open('gpurun_out/r02_c7_bench.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','e2e','gpu_launches','us_per_lockstep')}); print(d['roofline']['flop_form']); print(d['cpu_baseline']['value'], d['cpu_baseline']['cores'])
-"
-tail -3 gpurun_out/r02_c7_bench.err
+( timeout 600 python -m pytest tests/test_tacotron_gpu.py -q -x ) > gpurun_out/r02_c9_taco_tests.log 2>&1
+tail -15 gpurun_out/r02_c9_taco_tests.log
+( timeout 300 python bench.py --workload tacotron --steps 3 --warmup 2 --no-cpu-baseline ) > gpurun_out/r02_c9_taco.json 2> gpurun_out/r02_c9_taco.err
+cat gpurun_out/r02_c9_taco.json; tail -3 gpurun_out/r02_c9_taco.err
+( timeout 300 env B200TTS_GRID_PROF=1 python tools/quick_time.py grid 8,16,32 3000 ) > gpurun_out/r02_c9_push_time.log 2>&1
+tail -6 gpurun_out/r02_c9_push_time.log
