@@ -442,8 +442,10 @@ extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b
       pm.ncta = g.ncta; pm.R = R; pm.F = F; pm.NC = NC;
       int poff = 0;
       auto ptake = [&](int n) { int o = poff; poff += (n + 3) & ~3; return o; };
-      pm.ohh1 = ptake(12 * R); pm.oih2 = ptake(12 * R); pm.ohh2 = ptake(12 * R);
-      pm.ofc1 = ptake(4 * R); pm.ofc2 = ptake(4 * F); pm.ofc3 = ptake(8 * F);
+      // W_ih2 (12 rows) | fc1 (4 rows) | W_hh2 (12 rows) are contiguous: x1 is multiplied by the first 16 rows in one pass, h2 by the
+      // last 16 (fc1, then W_hh2) from one set of registers
+      pm.ohh1 = ptake(12 * R); pm.oih2 = ptake(12 * R); pm.ofc1 = ptake(4 * R); pm.ohh2 = ptake(12 * R);
+      pm.ofc2 = ptake(4 * F); pm.ofc3 = ptake(8 * F);
       pm.oAx = ptake(16); pm.obhh1 = ptake(12); pm.obhh2 = ptake(12); pm.obfc3 = ptake(8);
       pm.blob = poff;
       const size_t push_smem = ((size_t)pm.blob + (size_t)PushTraits<32>::scratch_floats(c.hop_length, NT)) * sizeof(float) + 1024;

@@ -164,7 +164,7 @@ template <int G> struct PushTraits {
   static constexpr int NKQ = kPushThreads / NU;            // k queues
   static constexpr int NKB = 128 / NKQ;                    // producer blocks (float4 columns) per thread and row
   static constexpr int NL = NKB * UT;                      // float4 loads per thread and vector = G/4
-  static constexpr int kPartFloats = kPushWarps * 12 * G;
+  static constexpr int kPartFloats = kPushWarps * 16 * G;        // up to 16 rows per pass (W_ih2 12 + fc1 4 on x1)
   static_assert(NU >= 4 && NU <= 32 && NKQ * NKB == 128 && NL * 4 == G && (32 / NU) * NKB == 8 && (NKB == 1 || NKB == 2 || NKB == 4), "mapping");
   // shared memory after the weight blob (floats)
   static constexpr int oPartX = 0;
@@ -184,9 +184,8 @@ template <int G> struct PushTraits {
 //      while it owns the pair, by warp shuffle otherwise; 8 consecutive kb per warp for every G), then the 16 warps in
 //      sequence (push_part_sum).  A row's result is therefore bit-identical whatever batch it is generated in (G = 4 ... 32),
 //      which is what lets N ranks reproduce the single-rank labels exactly.  Partials to part[(warp*ROWS + r)*G + u]. -------
-template <int G, int ROWS>
-__device__ __forceinline__ void push_gemm(const float* __restrict__ W /*[ROWS][512] smem*/, const float* vecbase, float* part,
-                                          int ul, int kq, int warp, int lane, PollGuard& pg) {
+template <int G>
+__device__ __forceinline__ void push_load(const float* vecbase, float4 (&a)[PushTraits<G>::NL], int ul, int kq, PollGuard& pg) {
   using PT = PushTraits<G>;
   constexpr int UT = PT::UT, NU = PT::NU, NKB = PT::NKB, NL = PT::NL;
   int off[NL];
@@ -194,10 +193,15 @@ __device__ __forceinline__ void push_gemm(const float* __restrict__ W /*[ROWS][5
   for (int i = 0; i < NKB; ++i)
 #pragma unroll
     for (int j = 0; j < UT; ++j) off[i * UT + j] = ((kq * NKB + i) * G + ul + NU * j) * 4;
-  float4 a[NL];
   poll_entries<NL>(vecbase, off, a, pg);
-  // (settling and multiplying block by block, so that the FMAs of block i overlap the loads of block i+1, was measured
-  //  SLOWER: 19.4 vs 14.4 us per step at 16 rows, 24.9 vs 21.7 at 32 -- the per-block leaves no longer fit the register file)
+}
+// (settling and multiplying block by block, so that the FMAs of block i overlap the loads of block i+1, was measured SLOWER:
+//  19.4 vs 14.4 us per step at 16 rows, 24.9 vs 21.7 at 32 -- the per-block leaves no longer fit the register file)
+template <int G, int ROWS>
+__device__ __forceinline__ void push_mma(const float* __restrict__ W /*[ROWS][512] smem*/, const float4 (&a)[PushTraits<G>::NL], float* part,
+                                         int ul, int kq, int warp, int lane) {
+  using PT = PushTraits<G>;
+  constexpr int UT = PT::UT, NU = PT::NU, NKB = PT::NKB;
   float acc[ROWS][UT];
   const float4* W4 = reinterpret_cast<const float4*>(W);
 #pragma unroll
@@ -241,6 +245,13 @@ __device__ __forceinline__ void push_gemm(const float* __restrict__ W /*[ROWS][5
 #pragma unroll
       for (int j = 0; j < UT; ++j) part[(warp * ROWS + r) * G + ul + NU * j] = acc[r][j];
   }
+}
+template <int G, int ROWS>
+__device__ __forceinline__ void push_gemm(const float* __restrict__ W /*[ROWS][512] smem*/, const float* vecbase, float* part,
+                                          int ul, int kq, int warp, int lane, PollGuard& pg) {
+  float4 a[PushTraits<G>::NL];
+  push_load<G>(vecbase, a, ul, kq, pg);
+  push_mma<G, ROWS>(W, a, part, ul, kq, warp, lane);
 }
 
 template <int G, int ROWS>
@@ -349,7 +360,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
   __syncthreads();
 
   PollGuard pg{A.error, 0, 0, false};
-  float h1own = 0.f, h2own = 0.f, x1own = 0.f;             // gate threads: state of unit 4c+gj, row gu
+  float h1own = 0.f, h2own = 0.f;                          // gate threads: state of unit 4c+gj, row gu
   __shared__ long long s_pf[12];                           // optional per-phase cycle counters of thread 0 (debug)
   __shared__ long long s_tmark;
   if (tid == 0) {
@@ -422,29 +433,34 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       const float h = gru_update(gir, giz, gin, gh1[gj * G + gu] + bhh[gj], gh1[(4 + gj) * G + gu] + bhh[4 + gj],
                                  gh1[(8 + gj) * G + gu] + bhh[8 + gj], h1own);
       h1own = h;
-      x1own = iout + h;
       const size_t e = ((size_t)c * G + gu) * 4 + gj;
       st_relaxed_f32(vecp(PV_H1, par) + e, h);
-      st_relaxed_f32(vecp(PV_X1, par) + e, x1own);
+      st_relaxed_f32(vecp(PV_X1, par) + e, iout + h);
     }
     __syncwarp();      // (4G < 32: lanes that skip the gate block must not run ahead into a spin loop and steal its issue slots)
     PUSH_MARK(1);
 
-    // ================= P2: GRU 2 input projection on x1(t) =================
-    push_gemm<G, 12>(Wb + M.oih2, vecp(PV_X1, par), partX, ul, kq, warp, lane, pg);
+    // ================= P2: W_ih2 (12 rows) AND fc1 (4 rows) on x1(t) =================
+    // x2 = x1 + h2 is never exchanged: fc1 . x2 = fc1 . x1 + fc1 . h2, the first half is taken here while x1 is in registers,
+    // the second in P3 from the h2 registers W_hh2 needs anyway -- one vector less through L2 per step.
+    float f1x = 0.f;                                          // gate threads: (fc1 . x1)[4c + gj] of row gu
+    {
+      float4 a[PT::NL];
+      push_load<G>(vecp(PV_X1, par), a, ul, kq, pg);
+      push_mma<G, 16>(Wb + M.oih2, a, partX, ul, kq, warp, lane);
+    }
     PUSH_MARK(2);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     if (gate) {
       const float* cd = cond20;
       const float* bhh = Wb + M.obhh2;
-      const float h = gru_update(push_part_sum<G, 12>(partX, gj, gu) + cd[gj * G + gu],
-                                 push_part_sum<G, 12>(partX, 4 + gj, gu) + cd[(4 + gj) * G + gu],
-                                 push_part_sum<G, 12>(partX, 8 + gj, gu) + cd[(8 + gj) * G + gu], gh2[gj * G + gu] + bhh[gj],
+      const float h = gru_update(push_part_sum<G, 16>(partX, gj, gu) + cd[gj * G + gu],
+                                 push_part_sum<G, 16>(partX, 4 + gj, gu) + cd[(4 + gj) * G + gu],
+                                 push_part_sum<G, 16>(partX, 8 + gj, gu) + cd[(8 + gj) * G + gu], gh2[gj * G + gu] + bhh[gj],
                                  gh2[(4 + gj) * G + gu] + bhh[4 + gj], gh2[(8 + gj) * G + gu] + bhh[8 + gj], h2own);
       h2own = h;
-      const size_t e = ((size_t)c * G + gu) * 4 + gj;
-      st_relaxed_f32(vecp(PV_H2, par) + e, h);
-      st_relaxed_f32(vecp(PV_X2, par) + e, x1own + h);
+      f1x = push_part_sum<G, 16>(partX, 12 + gj, gu);
+      st_relaxed_f32(vecp(PV_H2, par) + ((size_t)c * G + gu) * 4 + gj, h);
     }
     __syncwarp();
     PUSH_MARK(3);
@@ -454,17 +470,20 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
     for (int i = tid; i < 12 * G; i += kPushThreads) gh1[i] = push_part_sum<G, 12>(partY, i / G, i % G);
     PUSH_MARK(4);
 
-    // ================= P3: fc1 + relu on x2(t) =================
-    push_gemm<G, 4>(Wb + M.ofc1, vecp(PV_X2, par), partX, ul, kq, warp, lane, pg);
-    PUSH_MARK(5);
-    if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
-    if (gate) {
-      const float v = push_part_sum<G, 4>(partX, gj, gu) + cond20[(12 + gj) * G + gu];
-      st_relaxed_f32(vecp(PV_F1, par) + ((size_t)c * G + gu) * 4 + gj, fmaxf(v, 0.f));
+    // ================= P3: h2(t) once: fc1 (critical), then W_hh2 . h2(t) for step t+1 from the same registers =================
+    {
+      float4 a[PT::NL];
+      push_load<G>(vecp(PV_H2, par), a, ul, kq, pg);
+      push_mma<G, 4>(Wb + M.ofc1, a, partX, ul, kq, warp, lane);
+      PUSH_MARK(5);
+      if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
+      if (gate) {
+        const float v = (f1x + push_part_sum<G, 4>(partX, gj, gu)) + cond20[(12 + gj) * G + gu];
+        st_relaxed_f32(vecp(PV_F1, par) + ((size_t)c * G + gu) * 4 + gj, fmaxf(v, 0.f));
+      }
+      __syncwarp();
+      push_mma<G, 12>(Wb + M.ohh2, a, partY, ul, kq, warp, lane);
     }
-    __syncwarp();
-    // shadow: W_hh2 . h2(t) for step t+1
-    push_gemm<G, 12>(Wb + M.ohh2, vecp(PV_H2, par), partY, ul, kq, warp, lane, pg);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     for (int i = tid; i < 12 * G; i += kPushThreads) gh2[i] = push_part_sum<G, 12>(partY, i / G, i % G);
     PUSH_MARK(6);
@@ -485,7 +504,8 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       // step t+1 before it has seen THIS CTA's winner of step t, which is stored below after two block barriers that
       // follow this fence: the sentinels are performed gpu-wide by then.
 #pragma unroll
-      for (int v6 = 0; v6 < kPushVecs; ++v6) st_relaxed_u32(vecp(v6, par ^ 1) + e, kPushSentinel);
+      for (int v6 = 0; v6 < kPushVecs; ++v6)
+        if (v6 != PV_X2) st_relaxed_u32(vecp(v6, par ^ 1) + e, kPushSentinel);      // (x2 is not exchanged by this kernel)
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncwarp();
