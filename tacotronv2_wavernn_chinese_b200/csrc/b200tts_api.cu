@@ -862,8 +862,46 @@ static void check_grid_error(b200tts_wavernn* ctx) {
   REQUIRE(flag == 0, B200TTS_ECUDA, "grid kernel: a grid-barrier wait timed out (co-resident CTA missing); results are invalid");
 }
 
+static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
+                              const b200tts_gen_opts* opts, int16_t* d_labels, double* d_wave, cudaStream_t st);
+
+// The wide mapping streams a sample-rate mel buffer [S][feat][Bp] (1.8 GB at 256 rows x 80 frames, 22.5 GB at 256 x 1000): long
+// utterances x large batches would run out of memory before anything else.  Such a call is cut into row ranges whose buffers stay
+// under a budget (default 8 GB, env B200TTS_MAX_COND_BYTES); the noise is keyed by the global row, so the result is unchanged.
+// (Not for the debug modes whose buffers are indexed [step][row]: external noise, logits.)
 static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
                          const b200tts_gen_opts* opts, int16_t* d_labels, double* d_wave, cudaStream_t st) {
+  const double budget = getenv("B200TTS_MAX_COND_BYTES") ? atof(getenv("B200TTS_MAX_COND_BYTES")) : 8e9;   // read per call
+  const b200tts_wavernn_cfg& c = ctx->cfg;
+  const double per_row = (double)T * c.hop_length * c.feat_dims * sizeof(float);
+  const bool sliceable = B > 256 || per_row * 256 > budget;
+  const bool debug_bufs = (rng && rng->mode == B200TTS_RNG_EXT_EXPONENTIAL) || (opts && opts->d_logits);
+  const bool folding = opts && opts->fold_target > 0;
+  if (!sliceable || debug_bufs || folding || per_row * ((B + 255) / 256 * 256) <= budget || !d_labels) {
+    run_generate_rows(ctx, d_mel, B, T, rng, opts, d_labels, d_wave, st);
+    return;
+  }
+  int rows = (int)(budget / per_row);
+  rows = rows >= 256 ? rows / 256 * 256 : (rows >= 32 ? 32 : std::max(rows, 1));
+  const size_t S = (size_t)T * c.hop_length, wave_len = (size_t)(T - 1) * c.hop_length;
+  for (int r0 = 0; r0 < B; r0 += rows) {
+    const int nb = std::min(rows, B - r0);
+    b200tts_rng r{};
+    if (rng) r = *rng;
+    if (r.d_utterance_ids) r.d_utterance_ids += r0;
+    else r.utterance_offset += (uint64_t)r0;
+    b200tts_gen_opts o{};
+    if (opts) o = *opts;
+    else o.mu_law = 1;
+    if (o.d_teacher) o.d_teacher += (size_t)r0 * S;
+    if (o.d_utt_frames) o.d_utt_frames += r0;
+    run_generate_rows(ctx, d_mel + (size_t)r0 * c.feat_dims * T, nb, T, &r, &o, d_labels + (size_t)r0 * S,
+                      d_wave ? d_wave + (size_t)r0 * wave_len : nullptr, st);
+  }
+}
+
+static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
+                              const b200tts_gen_opts* opts, int16_t* d_labels, double* d_wave, cudaStream_t st) {
   const b200tts_wavernn_cfg& c = ctx->cfg;
   const int hop = c.hop_length, S = T * hop, O = c.res_out_dims;
   b200tts_gen_opts o{};

@@ -271,7 +271,8 @@ template <int G>
 __device__ __forceinline__ void push_cond16(const PushArgs& A, const float* fir_s, float* cdst, int c, int ncta, int t, int tid) {
   const size_t fstride = (size_t)ncta * kPushCondRows;
   const int fr0 = t / A.hop, ph0 = t - fr0 * A.hop;                   // row_stride == 0: every row is at the same frame / phase
-  for (int it = tid; it < 16 * G; it += kPushThreads) {
+  // items start at thread 4G: the gate threads (0 ... 4G-1) are busy with the fc2 gate, the re-arm and its fence at this point
+  for (int it = (tid + kPushThreads - 4 * G) % kPushThreads; it < 16 * G; it += kPushThreads) {
     const int u = it >> 4, r = it & 15;
     int src = u, fr = fr0, ph = ph0;
     bool beyond = false;
@@ -444,9 +445,14 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
     // x2 = x1 + h2 is never exchanged: fc1 . x2 = fc1 . x1 + fc1 . h2, the first half is taken here while x1 is in registers,
     // the second in P3 from the h2 registers W_hh2 needs anyway -- one vector less through L2 per step.
     float f1x = 0.f;                                          // gate threads: (fc1 . x1)[4c + gj] of row gu
+    // h1(t) was published together with x1(t): up to 16 rows (<= 4 float4 per vector and thread) its loads are issued with
+    // the x1 loads, so the W_hh1 pass below starts from registers instead of paying another L2 round trip
+    constexpr bool kPrefetchH1 = PT::NL <= 4;
+    float4 ah1[kPrefetchH1 ? PT::NL : 1];
     {
       float4 a[PT::NL];
       push_load<G>(vecp(PV_X1, par), a, ul, kq, pg);
+      if constexpr (kPrefetchH1) push_load<G>(vecp(PV_H1, par), ah1, ul, kq, pg);
       push_mma<G, 16>(Wb + M.oih2, a, partX, ul, kq, warp, lane);
     }
     PUSH_MARK(2);
@@ -465,7 +471,8 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
     __syncwarp();
     PUSH_MARK(3);
     // shadow: W_hh1 . h1(t) for step t+1
-    push_gemm<G, 12>(Wb + M.ohh1, vecp(PV_H1, par), partY, ul, kq, warp, lane, pg);
+    if constexpr (kPrefetchH1) push_mma<G, 12>(Wb + M.ohh1, reinterpret_cast<const float4 (&)[PT::NL]>(ah1), partY, ul, kq, warp, lane);
+    else push_gemm<G, 12>(Wb + M.ohh1, vecp(PV_H1, par), partY, ul, kq, warp, lane, pg);
     if (__syncthreads_or(pg.aborted ? 1 : 0)) return;
     for (int i = tid; i < 12 * G; i += kPushThreads) gh1[i] = push_part_sum<G, 12>(partY, i / G, i % G);
     PUSH_MARK(4);

@@ -66,29 +66,30 @@ def int_to_words(astr: str) -> str:
     return res
 
 
+# The reference's punctuation normalisation (:105-141) is a fixed sequence of literal and regex rewrites; kept here as data,
+# applied in order.  ('lit', a, b) = str.replace, ('re', pattern, b) = re.sub.
+_REWRITES = (
+    ('re', r'[）（]', ''),
+    ('lit', '：“', '，'), ('lit', '：', '，'), ('lit', '”！', '！'), ('lit', '”。', '。'),
+    ('lit', '……”', '。'), ('lit', '……', '。'), ('lit', '…。', '。'), ('lit', '…”', '。'), ('lit', '…', '。'), ('lit', '.', '。'),
+    ('lit', '”', ''), ('lit', '“', ''), ('lit', '、', '，'), ('lit', '-', '，'),
+    ('lit', '—', '，'), ('lit', '-', '，'), ('lit', '；', '。'),
+    ('re', r'，[，\s]+', '，'), ('re', r'。[。，\s]+', '。'), ('re', r'，。+', '。'),
+    ('re', r'？[？\s]+', '？'), ('re', r'，？+', '？'),
+    ('re', r'！[！\s]+', '！'), ('re', r'，！+', '！'),
+    ('re', r'\.+', '。'), ('re', r',+', '，'), ('re', r'!+', '！'), ('re', r'\?+', '？'),
+    ('re', r'\s+', ' '), ('lit', '|', ''),
+)
+_REWRITES_COMPILED = tuple((k, re.compile(a) if k == 're' else a, b) for k, a, b in _REWRITES)
+
+
 def preprocess(text: str, tone: bool = False) -> str:
-    """punctuation normalisation (:105-141)."""
+    """punctuation normalisation (:105-141): prosody marks dropped unless `tone`, lower-cased, `_REWRITES` in order, stripped."""
     if not tone:
         text = re.sub(r'#\d+', '', text)
     text = text.lower()
-    text = re.sub(r'[）（]', '', text)
-    text = text.replace('：“', '，').replace('：', '，').replace('”！', '！').replace('”。', '。')
-    text = text.replace('……”', '。').replace('……', '。').replace('…。', '。').replace('…”', '。').replace('…', '。').replace('.', '。')
-    text = text.replace('”', '').replace('“', '').replace('、', '，').replace('-', '，')
-    text = text.replace('—', '，').replace('-', '，').replace('；', '。')
-    text = re.sub(r'，[，\s]+', '，', text)
-    text = re.sub(r'。[。，\s]+', '。', text)
-    text = re.sub(r'，。+', '。', text)
-    text = re.sub(r'？[？\s]+', '？', text)
-    text = re.sub(r'，？+', '？', text)
-    text = re.sub(r'！[！\s]+', '！', text)
-    text = re.sub(r'，！+', '！', text)
-    text = re.sub(r'\.+', '。', text)
-    text = re.sub(r',+', '，', text)
-    text = re.sub(r'!+', '！', text)
-    text = re.sub(r'\?+', '？', text)
-    text = re.sub(r'\s+', ' ', text)
-    text = text.replace('|', '')
+    for kind, a, b in _REWRITES_COMPILED:
+        text = a.sub(b, text) if kind == 're' else text.replace(a, b)
     return text.strip()
 
 

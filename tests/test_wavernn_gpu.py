@@ -414,3 +414,22 @@ def test_push_kernel_result_is_independent_of_batch_size(torch_cuda):
         assert np.array_equal(part, full[:B]), f'rows generated {B} at a time differ from the same rows in a batch of 20'
     tail = eng.generate(mels[8:20], seed=5, utterance_offset=8, kernel='grid')['labels'].cpu().numpy()   # a "second rank's" shard
     assert np.array_equal(tail, full[8:20])
+
+
+def test_large_request_is_cut_into_row_ranges(torch_cuda):
+    """A batch whose sample-rate conditioning buffer would exceed the memory budget (wide mapping: S x 80 x rows floats; 22.5 GB
+    at 256 rows x 1000 frames) is run as several launches over row ranges.  The noise is keyed by the global row, so the labels
+    are those of the same row ranges generated by hand.  Budget forced down through B200TTS_MAX_COND_BYTES (read per call)."""
+    eng, _ = engine_for('synth5')
+    mels = synth.synth_mels(321, 100, 21)
+    os.environ['B200TTS_MAX_COND_BYTES'] = '100e6'          # 1.85 MB per row -> 54 rows fit -> ranges of 32 rows
+    try:
+        cut = eng.generate(mels, seed=4)
+    finally:
+        del os.environ['B200TTS_MAX_COND_BYTES']
+    lab, wave = cut['labels'].cpu().numpy(), cut['wave'].cpu().numpy()
+    for lo in range(0, 100, 32):
+        hi = min(lo + 32, 100)
+        part = eng.generate(mels[lo:hi], seed=4, utterance_offset=lo)
+        assert np.array_equal(part['labels'].cpu().numpy(), lab[lo:hi]), f'rows {lo}:{hi}'
+        np.testing.assert_array_equal(part['wave'].cpu().numpy(), wave[lo:hi])

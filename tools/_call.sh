@@ -1,6 +1,7 @@
 set -x
 mkdir -p gpurun_out
-( timeout 300 env B200TTS_GRID_PROF=1 python tools/quick_time.py grid 1,8,16,32 3000 ) > gpurun_out/r02_c12_push_time.log 2>&1
-tail -8 gpurun_out/r02_c12_push_time.log
-( timeout 900 python -m pytest tests/test_wavernn_gpu.py tests/test_sharded_gpu.py -q -x -k "mapping and (32 or 20 or 12 or 7 or 3) or fold or independent or shards or golden or config2 or philox or invariance" ) > gpurun_out/r02_c12_tests.log 2>&1
-tail -6 gpurun_out/r02_c12_tests.log
+N=$(nvidia-smi -L | wc -l)
+( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 3 --warmup 3 ) > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
+tail -c 2600 gpurun_out/r02_bench_n$N.json; tail -2 gpurun_out/r02_bench_n$N.err
+( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus $N --workload text2audio --steps 2 --warmup 1 ) > gpurun_out/r02_t2a_n$N.json 2> gpurun_out/r02_t2a_n$N.err
+tail -c 1200 gpurun_out/r02_t2a_n$N.json; tail -2 gpurun_out/r02_t2a_n$N.err
