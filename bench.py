@@ -336,7 +336,7 @@ def run_text2audio(args):
     import torch.distributed as dist
     from tacotronv2_wavernn_chinese_b200 import synth
     from tacotronv2_wavernn_chinese_b200.engine import WaveRNNEngine
-    from tacotronv2_wavernn_chinese_b200.pipeline import deal_round_robin, padded_lockstep_rows, plan_chunks, synthesize_sharded
+    from tacotronv2_wavernn_chinese_b200.pipeline import MIN_FRAMES, deal_round_robin, padded_lockstep_rows, plan_ragged, synthesize_sharded
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -367,8 +367,16 @@ def run_text2audio(args):
         frames = [int(m.shape[0]) for m in mels]
         shares = deal_round_robin(frames, world)
         done = need = 0
+        plans = []
         for sh in shares:
-            d, n = padded_lockstep_rows([frames[i] for i in sh], plan_chunks([frames[i] for i in sh], 32))
+            fr = [frames[i] for i in sh]
+            kind, plan = plan_ragged(fr, 32)
+            if kind == 'pack':
+                d, n = plan['rows'] * plan['steps'], sum(max(f, MIN_FRAMES) for f in fr) * HOP
+                plans.append(f"packed {plan['rows']} rows")
+            else:
+                d, n = padded_lockstep_rows(fr, plan)
+                plans.append(f'{len(plan)} chunk(s)')
             done, need = done + d, need + n
         dt = float(np.mean(times))
         print(json.dumps({
@@ -377,7 +385,8 @@ def run_text2audio(args):
             'data': 'train.txt sentences 1-64 (pinyin ids from tests/golden/taco_symbols.json), shipped Tacotron checkpoint, ' + wdesc,
             'config': {'workload': 'BASELINE config 5: tacotron_synthesize -> wavernn_gen in process, 64 sentences', 'sentences': 64,
                        'audio_seconds': total / 22050.0, 'mel_frames_min_max': [min(frames), max(frames)],
-                       'parallelism': f'sentences dealt round-robin by length over {world} GPU(s), length-sorted chunks of <= 32 rows per launch',
+                       'parallelism': f'sentences dealt round-robin by length over {world} GPU(s); per rank the cheaper of length-sorted chunks '
+                                      f'(<= 32 rows per launch) and packed rows (queues of utterances per kernel row): rank 0 = {plans[0]}',
                        'scheduler_rowsteps_computed_over_needed': done / max(1, need)},
             'rtf': dt / (total / 22050.0)}), flush=True)
     if world > 1:

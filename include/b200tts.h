@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200TTS_ABI_VERSION 2
+#define B200TTS_ABI_VERSION 3
 
 enum {
   B200TTS_OK = 0,
@@ -103,6 +103,16 @@ typedef struct {
   int32_t fold_overlap;       /* hp.voc_overlap                                                          */
   const int32_t* d_utt_frames;/* optional [B]: true frame count of each row of a zero-padded ragged batch; row b of d_wave is then
                                  truncated and faded at (frames_b - 1)*hop like a batch-1 run, and zero beyond      */
+  /* PACKED generation of a ragged set (ABI 3; no counterpart in the reference, which is batch-1).  The B utterances of d_mel are
+   * not one row each: `pack_rows` (<= 32) kernel rows each run a QUEUE of utterances back to back -- segment k of row r is
+   * utterance d_pack_utt[r*pack_segs + k] (< 0: none) and occupies lock-steps [d_pack_start[r*(pack_segs+1) + k],
+   * d_pack_start[r*(pack_segs+1) + k + 1]); a row restarts from the zero state (fatchord_version.py:194-196) at every segment
+   * start and the noise is keyed by (utterance, step within the utterance), so every utterance gets bit for bit the labels of a
+   * stand-alone run.  Lock-steps are spent on samples that are needed instead of on padding.  d_labels stays [B][S], d_wave
+   * [B][(T-1)*hop] (give d_utt_frames).  Requires the push kernel (rnn_dims = fc_dims = 512), PHILOX noise, no debug buffers. */
+  const int32_t* d_pack_utt;
+  const int32_t* d_pack_start;
+  int32_t pack_rows, pack_segs, pack_steps;   /* pack_steps = last segment end over all rows */
 } b200tts_gen_opts;
 
 typedef struct b200tts_wavernn b200tts_wavernn;

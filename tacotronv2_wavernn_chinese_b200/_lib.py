@@ -43,7 +43,9 @@ class Rng(C.Structure):
 
 class GenOpts(C.Structure):
     _fields_ = [('kernel', C.c_int32), ('mu_law', C.c_int32), ('d_teacher', C.c_void_p), ('d_logits', C.c_void_p),
-                ('max_steps', C.c_int32), ('fold_target', C.c_int32), ('fold_overlap', C.c_int32), ('d_utt_frames', C.c_void_p)]
+                ('max_steps', C.c_int32), ('fold_target', C.c_int32), ('fold_overlap', C.c_int32), ('d_utt_frames', C.c_void_p),
+                ('d_pack_utt', C.c_void_p), ('d_pack_start', C.c_void_p), ('pack_rows', C.c_int32), ('pack_segs', C.c_int32),
+                ('pack_steps', C.c_int32)]
 
 
 class TacoCfg(C.Structure):
@@ -111,7 +113,7 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
-            if lib.b200tts_abi_version() != 2:
+            if lib.b200tts_abi_version() != 3:
                 raise RuntimeError('libb200tts.so ABI version mismatch; rebuild it')
             _lib = lib
     return _lib

@@ -784,14 +784,20 @@ static bool push_eligible(const b200tts_wavernn* ctx, int rows) {
 
 // `fold` != null: rows are the folds of ONE source utterance of T0 frames (conditioning tables of utterance 0, row u
 // starts at sample u * stride); otherwise row u is utterance u.
-static void launch_push(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cudaStream_t st, const FoldGeom* fold, int T0) {
+struct PackInfo {            // gen_opts.d_pack_*: kernel rows run queues of utterances
+  const int* utt;
+  const int* start;
+  int rows, segs, steps, n_utt;
+};
+static void launch_push(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cudaStream_t st, const FoldGeom* fold, int T0,
+                        const PackInfo* pack = nullptr) {
   const b200tts_wavernn_cfg& c = ctx->cfg;
   const PushModel& pm = ctx->pm;
-  const int rows = ua.B;
+  const int rows = pack ? pack->rows : ua.B;
   const int ng = rows > kMgG ? (rows + kMgG - 1) / kMgG : 1;          // > 32 rows: multi-group kernel, groups of 32
   const int G = ng > 1 ? kMgG : push_rows(rows);
   const int T = fold ? T0 : ua.T, hop = c.hop_length;
-  const int tab_rows = fold ? 1 : ng * G, src_rows = fold ? 1 : rows;
+  const int tab_rows = fold ? 1 : (pack ? pack->n_utt : ng * G), src_rows = fold ? 1 : (pack ? pack->n_utt : rows);
   // conditioning tables [tab_rows][T+1][ncta][52]
   ctx->push_tab.ensure((size_t)tab_rows * (T + 1) * pm.ncta * kPushCondRows * sizeof(float));
   {
@@ -818,8 +824,9 @@ static void launch_push(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   a.tab = ctx->push_tab.as<float>();
   a.fir = ctx->d_fir;
   a.NT = ctx->NT;
-  a.B = rows; a.S = ua.S; a.T = T; a.hop = hop; a.steps = ua.steps;
+  a.B = pack ? pack->n_utt : rows; a.S = ua.S; a.T = T; a.hop = hop; a.steps = pack ? pack->steps : ua.steps;
   a.ng = ng;
+  if (pack) { a.pack_utt = pack->utt; a.pack_start = pack->start; a.pack_segs = pack->segs; a.pack_rows = pack->rows; }
   a.row_stride = fold ? fold->stride : 0;
   a.S_src = T * hop;
   a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.utt_ids = ua.utt_ids; a.q = ua.q;
@@ -877,7 +884,8 @@ static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T,
   const bool sliceable = B > 256 || per_row * 256 > budget;
   const bool debug_bufs = (rng && rng->mode == B200TTS_RNG_EXT_EXPONENTIAL) || (opts && opts->d_logits);
   const bool folding = opts && opts->fold_target > 0;
-  if (!sliceable || debug_bufs || folding || per_row * ((B + 255) / 256 * 256) <= budget || !d_labels) {
+  const bool packing = opts && opts->d_pack_utt;
+  if (!sliceable || debug_bufs || folding || packing || per_row * ((B + 255) / 256 * 256) <= budget || !d_labels) {
     run_generate_rows(ctx, d_mel, B, T, rng, opts, d_labels, d_wave, st);
     return;
   }
@@ -940,6 +948,13 @@ static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, i
     fg = fold_geometry(S, o.fold_target, o.fold_overlap);
     REQUIRE(fg.nfold >= 1 && fg.nfold <= 65535, B200TTS_EINVAL, "fold count out of range");
   }
+  const bool packing = o.d_pack_utt != nullptr;
+  if (packing) {
+    REQUIRE(!folding && o.d_pack_start && o.pack_rows >= 1 && o.pack_rows <= 32 && o.pack_segs >= 1 && o.pack_steps >= 1, B200TTS_EINVAL,
+            "bad packed-row schedule (pack_rows 1..32, pack_segs >= 1, pack_steps >= 1, not together with folding)");
+    REQUIRE(o.max_steps == 0 && !o.d_logits && !o.d_teacher && r.mode == B200TTS_RNG_PHILOX && d_labels, B200TTS_EINVAL,
+            "packed generation takes PHILOX noise, all steps, caller-owned labels and no debug buffers");
+  }
   const int GB = folding ? fg.nfold : B;            // rows the generation kernels see
   const int GS = folding ? fg.L : S;                // steps per row
   ctx->aux_frames.ensure((size_t)B * T * O * sizeof(float));
@@ -948,7 +963,8 @@ static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, i
     ctx->labels.ensure((size_t)GB * GS * sizeof(int16_t));
     labels = ctx->labels.as<int16_t>();
   }
-  const bool use_push = kernel == B200TTS_KERNEL_GRID && push_eligible(ctx, GB);
+  const bool use_push = kernel == B200TTS_KERNEL_GRID && push_eligible(ctx, packing ? o.pack_rows : GB);
+  REQUIRE(!packing || use_push, B200TTS_EINVAL, "packed generation needs the push kernel (kernel=auto/grid, rnn_dims = fc_dims = 512)");
   if (kernel == B200TTS_KERNEL_GRID && !ctx->gm.ok)
     throw Error(B200TTS_EINVAL, "kernel=grid was requested but this model/device cannot run the weight-stationary grid kernel "
                                 "(needs rnn_dims == fc_dims, n_classes == 2*rnn_dims, cooperative launch, R/4 <= SM count)");
@@ -991,7 +1007,8 @@ static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, i
     else launch_utt<8>(ctx, a, st);
     B200_CUDA(cudaEventRecord(ctx->ev1, st));
   } else if (use_push) {
-    launch_push(ctx, d_mel, a, st, folding ? &fg : nullptr, T);
+    PackInfo pi{o.d_pack_utt, o.d_pack_start, o.pack_rows, o.pack_segs, o.pack_steps, B};
+    launch_push(ctx, d_mel, a, st, folding ? &fg : nullptr, T, packing ? &pi : nullptr);
   } else {
     launch_grid(ctx, d_mel, a, st, folding ? &fg : nullptr, S);
   }

@@ -77,7 +77,27 @@ struct PushArgs {
   float* logits_out;             // [S][B][NC]
   int16_t* labels;               // [B][S]
   long long* prof;               // optional [ncta][16] cycle counters of thread 0
+  // PACKED rows (ragged sets, pipeline.py): row u runs a QUEUE of utterances back to back -- segment k of row u is utterance
+  // pack_utt[u*pack_segs + k] from step pack_start[u*(pack_segs+1) + k] (next entry = its end; utt < 0 = no more work) -- and
+  // restarts from the zero state at every segment start, so every utterance gets exactly the arithmetic of a stand-alone run.
+  // B then counts UTTERANCES (labels [B][S], tables [B][T+1]...), the kernel runs G rows for `steps` lock-steps.
+  const int* pack_utt;           // [pack_rows][pack_segs]
+  const int* pack_start;         // [pack_rows][pack_segs + 1]
+  int pack_segs, pack_rows;      // kernel rows >= pack_rows are idle
 };
+
+struct PushRowState {            // per-row bookkeeping in shared memory (normal mode: row u == utterance u from step 0, forever)
+  int utt[32], t0[32], end[32], k[32];     // current segment: utterance (-1 idle), first step, first step of the NEXT segment, index
+  int putt[32], pn[32];                    // (utterance, local step) the row was at in the PREVIOUS step (whose winner P01 collects)
+  int rst[32];                             // the current step is the first of a segment: x = 0, h1 = h2 = 0
+};
+// (utterance, local step) of row u at step t+1, seen from step t
+__device__ __forceinline__ void push_row_next(const PushArgs& A, const PushRowState& R, int u, int t1, int& utt, int& n) {
+  if (t1 < R.end[u]) { utt = R.utt[u]; n = t1 - R.t0[u]; return; }
+  const int k1 = R.k[u] + 1;
+  utt = (A.pack_utt && u < A.pack_rows && k1 < A.pack_segs) ? A.pack_utt[u * A.pack_segs + k1] : -1;
+  n = t1 - R.end[u];
+}
 
 // ---- L2-coherent accessors ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ld_relaxed_f4(const float* p) {
@@ -268,9 +288,10 @@ __device__ __forceinline__ float push_part_sum(const float* part, int r, int u) 
 // frame -> push_cond20, refreshed only when the next step starts a new frame (every step in fold mode, where rows sit at
 // different phases).
 template <int G>
-__device__ __forceinline__ void push_cond16(const PushArgs& A, const float* fir_s, float* cdst, int c, int ncta, int t, int tid) {
+__device__ __forceinline__ void push_cond16(const PushArgs& A, const PushRowState& R, const float* fir_s, float* cdst, int c, int ncta, int t,
+                                            int tid) {
   const size_t fstride = (size_t)ncta * kPushCondRows;
-  const int fr0 = t / A.hop, ph0 = t - fr0 * A.hop;                   // row_stride == 0: every row is at the same frame / phase
+  const int fr0 = t / A.hop, ph0 = t - fr0 * A.hop;                   // plain batch: every row is at the same frame / phase
   // items start at thread 4G: the gate threads (0 ... 4G-1) are busy with the fc2 gate, the re-arm and its fence at this point
   for (int it = (tid + kPushThreads - 4 * G) % kPushThreads; it < 16 * G; it += kPushThreads) {
     const int u = it >> 4, r = it & 15;
@@ -282,6 +303,12 @@ __device__ __forceinline__ void push_cond16(const PushArgs& A, const float* fir_
       beyond = n >= A.S_src;                                           // past the source utterance: zero mel and aux -> bias only
       fr = beyond ? A.T : (int)(n / A.hop);
       ph = beyond ? 0 : (int)(n - (long long)fr * A.hop);
+    } else if (A.pack_utt) {
+      int n;
+      push_row_next(A, R, u, t, src, n);
+      if (src < 0) { cdst[r * G + u] = 0.f; continue; }                // idle row
+      fr = n / A.hop;
+      ph = n - fr * A.hop;
     }
     const float* row = A.tab + (((size_t)src * (A.T + 1) + fr) * ncta + c) * kPushCondRows;
     float v = __ldg(row + 16 + r);
@@ -298,7 +325,7 @@ __device__ __forceinline__ void push_cond16(const PushArgs& A, const float* fir_
   }
 }
 template <int G>
-__device__ __forceinline__ void push_cond20(const PushArgs& A, float* cdst, int c, int ncta, int t, int tid) {
+__device__ __forceinline__ void push_cond20(const PushArgs& A, const PushRowState& R, float* cdst, int c, int ncta, int t, int tid) {
   const int fr0 = t / A.hop;
   for (int it = tid; it < 20 * G; it += kPushThreads) {
     const int u = it / 20, r = it - u * 20;
@@ -307,6 +334,11 @@ __device__ __forceinline__ void push_cond20(const PushArgs& A, float* cdst, int 
       const long long n = (long long)u * A.row_stride + t;
       src = 0;
       fr = n >= A.S_src ? A.T : (int)(n / A.hop);
+    } else if (A.pack_utt) {
+      int n;
+      push_row_next(A, R, u, t, src, n);
+      if (src < 0) { cdst[r * G + u] = 0.f; continue; }
+      fr = n / A.hop;
     }
     cdst[r * G + u] = __ldg(A.tab + (((size_t)src * (A.T + 1) + fr) * ncta + c) * kPushCondRows + 32 + r);
   }
@@ -353,11 +385,27 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
   }
   for (int i = tid; i < A.hop * A.NT; i += kPushThreads) fir_s[i] = A.fir[i];
   for (int i = tid; i < 12 * G; i += kPushThreads) { gh1[i] = 0.f; gh2[i] = 0.f; }     // W_hh . 0  (h1 = h2 = 0, :194-195)
+  __shared__ PushRowState R;
+  if (tid < G) {
+    // state "before step 0": an empty segment ending at step 0, so that push_row_next(..., t = 0) finds segment 0
+    R.k[tid] = -1; R.utt[tid] = -1; R.t0[tid] = 0; R.end[tid] = 0; R.putt[tid] = -1; R.pn[tid] = 0; R.rst[tid] = 1;
+    if (!A.pack_utt) {                                     // plain batch / folds: row u is utterance u from step 0 to the end
+      R.k[tid] = 0; R.utt[tid] = tid < A.B ? tid : -1; R.end[tid] = 0x7fffffff;
+    }
+  }
   __syncthreads();
   float* cond16 = cond;                       // [2][16][G]  rows 0-15 of step t (parity buffers, written one step ahead)
   float* cond20 = cond + 2 * 16 * G;          // [20][G]     rows 16-35 of the current frame
-  push_cond16<G>(A, fir_s, cond16, c, ncta, 0, tid);
-  push_cond20<G>(A, cond20, c, ncta, 0, tid);
+  push_cond16<G>(A, R, fir_s, cond16, c, ncta, 0, tid);
+  push_cond20<G>(A, R, cond20, c, ncta, 0, tid);
+  __syncthreads();
+  if (A.pack_utt && tid < G) {                             // enter segment 0 (kernel rows beyond the schedule stay idle)
+    const bool live = tid < A.pack_rows && A.pack_segs > 0;
+    R.k[tid] = 0;
+    R.utt[tid] = live ? A.pack_utt[tid * A.pack_segs] : -1;
+    R.t0[tid] = 0;
+    R.end[tid] = live ? A.pack_start[tid * (A.pack_segs + 1) + 1] : 0x7fffffff;
+  }
   __syncthreads();
 
   PollGuard pg{A.error, 0, 0, false};
@@ -415,15 +463,18 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
 #pragma unroll
         for (int w = 0; w < kPushWarps; ++w) { const unsigned long long v = smax[w * G + gu]; b = v > b ? v : b; }
         const int label = (int)push_cls(b);
-        if (gu < A.B) {
-          if (c == 0 && gj == 0) A.labels[(size_t)gu * A.S + (t - 1)] = (int16_t)label;
-          const int fb = A.teacher ? (int)A.teacher[(size_t)gu * A.S + (t - 1)] : label;
+        const int putt = R.putt[gu], pn = R.pn[gu];         // where this row was at step t-1
+        if (putt >= 0) {
+          if (c == 0 && gj == 0) A.labels[(size_t)putt * A.S + pn] = (int16_t)label;
+          const int fb = A.teacher ? (int)A.teacher[(size_t)putt * A.S + pn] : label;
           x = label_to_float(fb, ncls_m1);
         }
       }
     }
     if (t == A.steps) break;                                // the extra trip only collects the last winner
+    const bool restart = gate && R.rst[gu] != 0;            // first step of an utterance: x = 0, h1 = h2 = 0 (:194-196)
     if (gate) {
+      if (restart) { x = 0.f; h1own = 0.f; }
       const float* cd = cond16 + par * 16 * G;
       const float* wAx = Wb + M.oAx;
       const float* bhh = Wb + M.obhh1;
@@ -431,8 +482,9 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       const float gir = fmaf(wAx[4 + gj], x, cd[(4 + gj) * G + gu]);
       const float giz = fmaf(wAx[8 + gj], x, cd[(8 + gj) * G + gu]);
       const float gin = fmaf(wAx[12 + gj], x, cd[(12 + gj) * G + gu]);
-      const float h = gru_update(gir, giz, gin, gh1[gj * G + gu] + bhh[gj], gh1[(4 + gj) * G + gu] + bhh[4 + gj],
-                                 gh1[(8 + gj) * G + gu] + bhh[8 + gj], h1own);
+      const float g1r = restart ? 0.f : gh1[gj * G + gu], g1z = restart ? 0.f : gh1[(4 + gj) * G + gu],
+                  g1n = restart ? 0.f : gh1[(8 + gj) * G + gu];            // W_hh1 . 0
+      const float h = gru_update(gir, giz, gin, g1r + bhh[gj], g1z + bhh[4 + gj], g1n + bhh[8 + gj], h1own);
       h1own = h;
       const size_t e = ((size_t)c * G + gu) * 4 + gj;
       st_relaxed_f32(vecp(PV_H1, par) + e, h);
@@ -460,10 +512,13 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
     if (gate) {
       const float* cd = cond20;
       const float* bhh = Wb + M.obhh2;
+      if (restart) h2own = 0.f;
+      const float g2r = restart ? 0.f : gh2[gj * G + gu], g2z = restart ? 0.f : gh2[(4 + gj) * G + gu],
+                  g2n = restart ? 0.f : gh2[(8 + gj) * G + gu];            // W_hh2 . 0
       const float h = gru_update(push_part_sum<G, 16>(partX, gj, gu) + cd[gj * G + gu],
                                  push_part_sum<G, 16>(partX, 4 + gj, gu) + cd[(4 + gj) * G + gu],
-                                 push_part_sum<G, 16>(partX, 8 + gj, gu) + cd[(8 + gj) * G + gu], gh2[gj * G + gu] + bhh[gj],
-                                 gh2[(4 + gj) * G + gu] + bhh[4 + gj], gh2[(8 + gj) * G + gu] + bhh[8 + gj], h2own);
+                                 push_part_sum<G, 16>(partX, 8 + gj, gu) + cd[(8 + gj) * G + gu], g2r + bhh[gj], g2z + bhh[4 + gj],
+                                 g2n + bhh[8 + gj], h2own);
       h2own = h;
       f1x = push_part_sum<G, 16>(partX, 12 + gj, gu);
       st_relaxed_f32(vecp(PV_H2, par) + ((size_t)c * G + gu) * 4 + gj, h);
@@ -518,8 +573,8 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
     __syncwarp();
     // shadow: conditioning of step t+1 (rows 0-15 into the other parity buffer; rows 16-35 only when a new frame starts)
     if (t + 1 < A.steps) {
-      push_cond16<G>(A, fir_s, cond16 + (par ^ 1) * 16 * G, c, ncta, t + 1, tid);
-      if (A.row_stride || (t + 1) % A.hop == 0) push_cond20<G>(A, cond20, c, ncta, t + 1, tid);
+      push_cond16<G>(A, R, fir_s, cond16 + (par ^ 1) * 16 * G, c, ncta, t + 1, tid);
+      if (A.row_stride || A.pack_utt || (t + 1) % A.hop == 0) push_cond20<G>(A, R, cond20, c, ncta, t + 1, tid);
     }
     PUSH_MARK(8);
 
@@ -532,15 +587,16 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
       const int cls = c * kCPC + r;
       const float l = push_part_sum<G, 8>(partY, r, u) + Wb[M.obfc3 + r];
       float qv = 1.0f;
-      if (u < A.B) {
+      const int utt = R.utt[u], n = t - R.t0[u];               // plain batch: utt == u, n == t
+      if (utt >= 0) {
         if (A.rng_mode == 0) {
           float q4[4];
-          philox_exp4(A.seed, A.utt_ids ? A.utt_ids[u] : A.utt_offset + (unsigned long long)u, (uint32_t)t, (uint32_t)(cls >> 2), q4);
+          philox_exp4(A.seed, A.utt_ids ? A.utt_ids[utt] : A.utt_offset + (unsigned long long)utt, (uint32_t)n, (uint32_t)(cls >> 2), q4);
           qv = q4[cls & 3];
         } else {
-          qv = __ldg(A.q + ((size_t)t * A.B + u) * M.NC + cls);
+          qv = __ldg(A.q + ((size_t)n * A.B + utt) * M.NC + cls);
         }
-        if (A.logits_out) A.logits_out[((size_t)t * A.B + u) * M.NC + cls] = l;
+        if (A.logits_out) A.logits_out[((size_t)n * A.B + utt) * M.NC + cls] = l;
       }
       skeys[r * G + u] = push_pack(l - logf(qv), (uint32_t)cls, (uint32_t)(t + 1));
     }
@@ -550,6 +606,20 @@ __global__ void __launch_bounds__(kPushThreads, 1) wavernn_push_kernel(PushModel
 #pragma unroll
       for (int r = 1; r < 8; ++r) { const unsigned long long v = skeys[r * G + tid]; b = v > b ? v : b; }
       st_relaxed_u64(A.best + (size_t)c * G + tid, b);
+      // row bookkeeping for step t+1 (read by the gate threads after the barrier of the next winner poll)
+      R.putt[tid] = R.utt[tid];
+      R.pn[tid] = t - R.t0[tid];
+      int rst = 0;
+      if (t + 1 >= R.end[tid]) {                               // the row's utterance ends with this step: enter its next segment
+        const int k1 = R.k[tid] + 1, e0 = R.end[tid];
+        R.k[tid] = k1;
+        const bool more = A.pack_utt && tid < A.pack_rows && k1 < A.pack_segs;
+        R.utt[tid] = more ? A.pack_utt[tid * A.pack_segs + k1] : -1;
+        R.t0[tid] = e0;
+        R.end[tid] = more ? A.pack_start[tid * (A.pack_segs + 1) + k1 + 1] : 0x7fffffff;
+        rst = 1;
+      }
+      R.rst[tid] = rst;
     }
     __syncwarp();
     PUSH_MARK(10);

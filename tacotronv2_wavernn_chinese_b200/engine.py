@@ -99,11 +99,13 @@ class WaveRNNEngine:
 
     def generate(self, mels, *, seed: int = 0, utterance_offset: int = 0, utterance_ids=None, q=None, teacher=None,
                  return_logits: bool = False, want_wave: bool = True, mu_law: bool = True, kernel: str = 'auto',
-                 max_steps: int = 0, fold=None, utt_frames=None):
+                 max_steps: int = 0, fold=None, utt_frames=None, pack=None):
         """Runs the generation loop on the device.
 
         Returns dict(labels int16 [B,S] cuda, wave float64 [B,wave_len] cuda or None, logits [S,B,NC] or None).
         q: optional Exp(1) noise [S,B,NC] (torch/numpy) -> EXT_EXPONENTIAL mode; otherwise PHILOX(seed).
+        pack: optional packed-row schedule dict(rows, utt int32 [rows, segs], start int32 [rows, segs+1], steps) from
+        pipeline.pack_schedule: `rows` kernel rows run queues of the B utterances back to back (gen_opts.d_pack_*).
         """
         m = self._mel(mels)
         B, _, T = m.shape
@@ -144,6 +146,15 @@ class WaveRNNEngine:
             opts.max_steps = int(max_steps)
             if fold is not None:
                 opts.fold_target, opts.fold_overlap = int(fold[0]), int(fold[1])
+            pk_u = pk_s = None
+            if pack is not None:
+                pk_u = torch.as_tensor(np.ascontiguousarray(pack['utt'], dtype=np.int32)).to(dev)
+                pk_s = torch.as_tensor(np.ascontiguousarray(pack['start'], dtype=np.int32)).to(dev)
+                rows, segs = pk_u.shape
+                if tuple(pk_s.shape) != (rows, segs + 1) or rows != int(pack['rows']):
+                    raise ValueError('pack: utt must be [rows, segs], start [rows, segs + 1]')
+                opts.d_pack_utt, opts.d_pack_start = pk_u.data_ptr(), pk_s.data_ptr()
+                opts.pack_rows, opts.pack_segs, opts.pack_steps = rows, segs, int(pack['steps'])
             uf = None
             if utt_frames is not None:
                 uf = torch.as_tensor(utt_frames).to(device=dev, dtype=torch.int32).contiguous()
@@ -163,7 +174,7 @@ class WaveRNNEngine:
             _lib.check(self.lib.b200tts_wavernn_generate(self._h, _ptr(m), B, T, C.byref(rng), C.byref(opts),
                                                          _ptr(labels), _ptr(wave), self._stream()))
             # keep inputs alive until the stream has consumed them
-            for t in (m, qd, td, uf, ids):
+            for t in (m, qd, td, uf, ids, pk_u, pk_s):
                 if t is not None:
                     t.record_stream(torch.cuda.current_stream(self.device))
         return dict(labels=labels, wave=wave, logits=logits, steps=steps)

@@ -9,6 +9,9 @@ and below ~32 rows it barely depends on the row count at all, so
   * the vocoder runs LENGTH-SORTED CHUNKS of at most `max_rows` rows (one launch each, padded only to the longest mel of the
     chunk; every row is truncated / faded at its own length, `gen_opts.d_utt_frames`) -- the padded lock-steps of a 64-sentence
     set drop from (longest - mean) x 64 to the spread inside each chunk;
+  * or, when cheaper by the measured step times, PACKED ROWS: one launch whose 8 / 16 / 32 kernel rows each run a queue of
+    utterances back to back (longest-processing-time list scheduling, `gen_opts.d_pack_*`), the row restarting from the zero
+    state at every utterance start -- no lock-step is spent on padding and a short queue can use a faster, narrower kernel;
   * across ranks the sentences are dealt round-robin in order of decreasing length, so every rank gets the same
     length profile and the makespan is the longest sentence's;
   * the sampling noise and the prenet dropout are keyed by the GLOBAL sentence index (`rng.d_utterance_ids`), so a
@@ -44,16 +47,77 @@ def padded_lockstep_rows(frames, chunks, hop=275):
     return done, need
 
 
-def vocode_ragged(voc, mels, ids, seed=0, max_rows=32, kernel='auto'):
+# us per lock-step of the push kernel by row count (B200, profiles/r02_push_v5_phase_cycles.txt): the scheduler's cost model
+STEP_US = {8: 9.0, 16: 14.5, 32: 20.6}
+
+
+def pack_schedule(frames, rows, hop=275):
+    """Longest-processing-time list scheduling of utterances onto `rows` kernel rows: every utterance (longest first) goes to
+    the row that frees first.  Returns dict(rows, utt [rows, segs], start [rows, segs + 1], steps) for gen_opts.d_pack_*:
+    row r runs utterance utt[r, k] during lock-steps [start[r, k], start[r, k+1]); unused slots: utt = -1, start = 2^31 - 1."""
+    order = sorted(range(len(frames)), key=lambda i: (-int(frames[i]), i))
+    queue = [[] for _ in range(rows)]
+    load = [0] * rows
+    for i in order:
+        r = min(range(rows), key=lambda j: (load[j], j))
+        queue[r].append(i)
+        load[r] += max(int(frames[i]), MIN_FRAMES) * hop
+    segs = max(1, max(len(q) for q in queue))
+    big = 2 ** 31 - 1
+    utt = np.full((rows, segs), -1, dtype=np.int32)
+    start = np.full((rows, segs + 1), big, dtype=np.int32)
+    for r, q in enumerate(queue):
+        t = 0
+        start[r, 0] = 0
+        for k, i in enumerate(q):
+            utt[r, k] = i
+            t += max(int(frames[i]), MIN_FRAMES) * hop
+            start[r, k + 1] = t
+    return dict(rows=rows, utt=utt, start=start, steps=int(max(load)), queue=queue)
+
+
+def plan_ragged(frames, max_rows=32, hop=275):
+    """Cheapest of: length-sorted chunks (one utterance per row, padded to the chunk's longest) and packed rows at 8 / 16 / 32
+    rows, by the measured step times.  Returns ('chunks', chunk list) or ('pack', schedule)."""
+    step = lambda rows: STEP_US[8 if rows <= 8 else (16 if rows <= 16 else 32)]
+    chunks = plan_chunks(frames, max_rows)
+    best = ('chunks', chunks)
+    best_us = sum(max(max(int(frames[i]) for i in c), MIN_FRAMES) * hop * step(len(c)) for c in chunks)
+    for rows in (8, 16, 32):
+        if rows > max_rows or rows >= 2 * len(frames):
+            continue
+        sch = pack_schedule(frames, rows, hop)
+        us = sch['steps'] * step(rows)
+        if us < 0.97 * best_us:
+            best, best_us = ('pack', sch), us
+    return best
+
+
+def vocode_ragged(voc, mels, ids, seed=0, max_rows=32, kernel='auto', allow_pack=True):
     """mels: list of float32 [T_b, 80] in [0, 1]; ids: global sentence index of each (keys the sampling noise).
     Returns the list of float64 waves [(max(T_b, 21) - 1) * hop] in the order given."""
     n = len(mels)
     if n == 0:
         return []
     frames = [int(m.shape[0]) for m in mels]
+    kind, plan = plan_ragged(frames, max_rows, voc.hop) if allow_pack else ('chunks', plan_chunks(frames, max_rows))
+    if kind == 'pack':
+        # ONE launch: `rows` kernel rows run queues of utterances back to back (state reset at every utterance start)
+        T = max(max(frames), MIN_FRAMES)
+        feat = mels[0].shape[1]
+        batch = np.zeros((n, feat, T), dtype=np.float32)
+        uf = np.zeros(n, dtype=np.int32)
+        for i, m in enumerate(mels):
+            batch[i, :, :frames[i]] = m.T
+            uf[i] = max(frames[i], MIN_FRAMES)
+        out = voc.generate(torch.as_tensor(batch), seed=seed, utterance_ids=[int(i) for i in ids], kernel=kernel, utt_frames=uf,
+                           pack=plan)
+        wave = out['wave'].cpu().numpy()
+        voc.check()
+        return [wave[i, :(uf[i] - 1) * voc.hop].copy() for i in range(n)]
     waves = [None] * n
     feat = mels[0].shape[1]
-    for chunk in plan_chunks(frames, max_rows):
+    for chunk in plan:
         T = max(max(frames[i] for i in chunk), MIN_FRAMES)
         batch = np.zeros((len(chunk), feat, T), dtype=np.float32)      # zero frames past the end == the reference's own padding
         uf = np.zeros(len(chunk), dtype=np.int32)
@@ -69,12 +133,12 @@ def vocode_ragged(voc, mels, ids, seed=0, max_rows=32, kernel='auto'):
     return waves
 
 
-def synthesize_batch(synth, wavernn_engine, texts, seed=0, utterance_offset=0, kernel='auto', max_rows=32):
+def synthesize_batch(synth, wavernn_engine, texts, seed=0, utterance_offset=0, kernel='auto', max_rows=32, allow_pack=True):
     """synth: tacotron.synthesizer.Synthesizer (loaded); wavernn_engine: engine.WaveRNNEngine; texts: pinyin strings.
     Returns (list of float64 waves, list of mels [T_b, 80]) for sentences utterance_offset ... of a larger set."""
     mels, _ = synth.mels(texts, seed=seed, utterance_offset=utterance_offset)
     ids = [utterance_offset + b for b in range(len(mels))]
-    return vocode_ragged(wavernn_engine, mels, ids, seed=seed, max_rows=max_rows, kernel=kernel), list(mels)
+    return vocode_ragged(wavernn_engine, mels, ids, seed=seed, max_rows=max_rows, kernel=kernel, allow_pack=allow_pack), list(mels)
 
 
 def synthesize_sharded(synth, wavernn_engine, texts, seed=0, group=None, kernel='auto', max_rows=32):

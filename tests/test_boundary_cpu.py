@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f'{name} declared in b200tts.h but not exported'
     assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
-    assert lib.b200tts_abi_version() == 2
+    assert lib.b200tts_abi_version() == 3
 
 
 def test_library_is_sm100a_and_has_no_cpu_path():
@@ -53,7 +53,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(L.WaveRNNCfg) == 14 * 4
     assert ctypes.sizeof(L.Tensor) == 8 + 8 + 8 + 32
     assert ctypes.sizeof(L.Rng) == 40          # ABI 2: + d_utterance_ids
-    assert ctypes.sizeof(L.GenOpts) == 48
+    assert ctypes.sizeof(L.GenOpts) == 80          # ABI 3: + packed-row schedule
 
 
 def test_hparams_singleton_contract(tmp_path):

@@ -34,9 +34,9 @@ class FakeVoc:
     def __init__(self):
         self.calls = []
 
-    def generate(self, mels, seed=0, utterance_ids=None, kernel='auto', utt_frames=None):
+    def generate(self, mels, seed=0, utterance_ids=None, kernel='auto', utt_frames=None, pack=None):
         B, _, T = mels.shape
-        self.calls.append((B, T))
+        self.calls.append((B, T) if pack is None else ('pack', pack['rows'], B, T))
         wave = torch.zeros(B, (T - 1) * HOP, dtype=torch.float64)
         for r in range(B):
             n = (int(utt_frames[r]) - 1) * HOP
@@ -65,12 +65,41 @@ def test_plan_chunks_and_deal():
     assert max(len(s) for s in shares) - min(len(s) for s in shares) <= 1
 
 
+def test_pack_schedule_is_a_valid_lpt_plan():
+    for rows in (2, 8):
+        sch = pl.pack_schedule(FRAMES, rows)
+        utt, start = sch['utt'], sch['start']
+        assert utt.shape[0] == rows and start.shape == (rows, utt.shape[1] + 1) and utt.dtype == np.int32
+        seen = []
+        for r in range(rows):
+            assert start[r, 0] == 0
+            for k in range(utt.shape[1]):
+                if utt[r, k] >= 0:
+                    seen.append(int(utt[r, k]))
+                    assert start[r, k + 1] - start[r, k] == max(FRAMES[utt[r, k]], 21) * HOP       # a whole utterance, back to back
+                else:
+                    assert (utt[r, k:] < 0).all() and (start[r, k + 1:] == 2 ** 31 - 1).all()
+        assert sorted(seen) == list(range(len(FRAMES)))
+        ends = [max(int(start[r, k + 1]) for k in range(utt.shape[1]) if utt[r, k] >= 0) for r in range(rows) if utt[r, 0] >= 0]
+        assert sch['steps'] == max(ends)
+        # list scheduling bound: makespan <= mean load + longest job
+        total = sum(max(f, 21) for f in FRAMES) * HOP
+        assert sch['steps'] <= total / rows + max(FRAMES) * HOP
+    kind, plan = pl.plan_ragged(FRAMES, 32)                 # 11 ragged sentences: 8 packed rows beat one 16-row padded launch
+    assert kind == 'pack' and plan['rows'] == 8
+    assert pl.plan_ragged([300] * 8, 32)[0] == 'chunks'     # nothing to gain when every row holds one equally long utterance
+
+
 def test_vocode_ragged_is_independent_of_chunking():
     mels, _ = FakeSynth(FRAMES).mels([''] * len(FRAMES))
     ids = list(range(len(FRAMES)))
-    a = pl.vocode_ragged(FakeVoc(), mels, ids, seed=3, max_rows=32)
+    a = pl.vocode_ragged(FakeVoc(), mels, ids, seed=3, max_rows=32, allow_pack=False)
+    pk = FakeVoc()
+    p2 = pl.vocode_ragged(pk, mels, ids, seed=3, max_rows=32)
+    assert pk.calls == [('pack', 8, len(FRAMES), 410)]
     voc = FakeVoc()
     b = pl.vocode_ragged(voc, mels, ids, seed=3, max_rows=3)
+    assert all(np.array_equal(x, y) for x, y in zip(a, p2))
     assert len(voc.calls) == 4 and voc.calls[0] == (3, 410)
     for i, (x, y) in enumerate(zip(a, b)):
         assert x.shape == ((max(FRAMES[i], 21) - 1) * HOP,) and np.array_equal(x, y)

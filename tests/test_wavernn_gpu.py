@@ -433,3 +433,29 @@ def test_large_request_is_cut_into_row_ranges(torch_cuda):
         part = eng.generate(mels[lo:hi], seed=4, utterance_offset=lo)
         assert np.array_equal(part['labels'].cpu().numpy(), lab[lo:hi]), f'rows {lo}:{hi}'
         np.testing.assert_array_equal(part['wave'].cpu().numpy(), wave[lo:hi])
+
+
+def test_packed_rows_equal_standalone_utterances(torch_cuda):
+    """Packed generation of a ragged set (gen_opts.d_pack_*): 2 / 8 kernel rows each run a queue of utterances back to back and
+    restart from the zero state at every utterance start.  Every utterance must come out BIT FOR BIT as from a stand-alone run
+    (same noise key, same arithmetic) -- labels over its full length and the truncated / faded wave.  Shipped checkpoint."""
+    from tacotronv2_wavernn_chinese_b200 import pipeline as pl
+    eng, _ = engine_for('ckpt')
+    frames = [60, 25, 40, 21, 33, 52, 30, 47, 22, 36, 28]
+    T = max(frames)
+    ids = [100 + 3 * i for i in range(len(frames))]                     # arbitrary global utterance indices
+    full = synth.synth_mels(808, len(frames), T)
+    batch = np.zeros_like(full)
+    for i, f in enumerate(frames):
+        batch[i, :, :f] = full[i, :, :f]                                # zero frames past each utterance's end
+    solo = [eng.generate(batch[i:i + 1, :, :f], seed=21, utterance_ids=[ids[i]]) for i, f in enumerate(frames)]
+    for rows in (2, 8):
+        sch = pl.pack_schedule(frames, rows)
+        assert sch['steps'] < sum(frames) * 275                         # really several utterances per row
+        out = eng.generate(batch, seed=21, utterance_ids=ids, utt_frames=np.array(frames, np.int32), pack=sch)
+        eng.check()
+        lab, wave = out['labels'].cpu().numpy(), out['wave'].cpu().numpy()
+        for i, f in enumerate(frames):
+            assert np.array_equal(lab[i, :f * 275], solo[i]['labels'].cpu().numpy()[0]), f'rows={rows}: utterance {i} ({f} frames)'
+            np.testing.assert_array_equal(wave[i, :(f - 1) * 275], solo[i]['wave'].cpu().numpy()[0])
+            assert np.all(wave[i, (f - 1) * 275:] == 0.0)
