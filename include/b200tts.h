@@ -89,7 +89,8 @@ typedef struct {
 enum {
   B200TTS_KERNEL_AUTO = 0,
   B200TTS_KERNEL_UTTERANCE = 1, /* one CTA per group of utterances, weights streamed from L2      */
-  B200TTS_KERNEL_GRID = 2       /* weight-stationary persistent cooperative grid, all SMs per step */
+  B200TTS_KERNEL_GRID = 2,      /* weight-stationary persistent cooperative grid, all SMs per step */
+  B200TTS_KERNEL_TC = 3         /* layer-stationary tensor-core pipeline (tcgen05, split-fp16 operands), 33-256 rows */
 };
 typedef struct {
   int32_t kernel;             /* B200TTS_KERNEL_*                                                      */

@@ -15,8 +15,8 @@ from .build import LIB
 
 OK = 0
 RNG_PHILOX, RNG_EXT_EXPONENTIAL = 0, 1
-KERNEL_AUTO, KERNEL_UTTERANCE, KERNEL_GRID = 0, 1, 2
-KERNELS = {'auto': KERNEL_AUTO, 'utterance': KERNEL_UTTERANCE, 'grid': KERNEL_GRID}
+KERNEL_AUTO, KERNEL_UTTERANCE, KERNEL_GRID, KERNEL_TC = 0, 1, 2, 3
+KERNELS = {'auto': KERNEL_AUTO, 'utterance': KERNEL_UTTERANCE, 'grid': KERNEL_GRID, 'tc': KERNEL_TC}
 
 
 class B200TTSError(RuntimeError):

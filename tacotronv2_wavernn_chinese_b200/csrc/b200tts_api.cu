@@ -17,6 +17,7 @@
 #include "wavernn_grid.cuh"
 #include "wavernn_push.cuh"
 #include "wavernn_pushmg.cuh"
+#include "wavernn_tc.cuh"
 #include "taco_decoder.cuh"
 #include "taco_encpost.cuh"
 #include "taco_grid.cuh"
@@ -160,6 +161,8 @@ struct b200tts_wavernn {
   PushModel pm{};                 // small-batch push kernel (wavernn_push.cuh): per-CTA blobs + conditioning-projection weights
   PushCondW pcw{};
   DeviceBuf push_blob, push_condw, push_tab, push_vec, push_best, push_prof;
+  DeviceBuf tc_wimg, tc_prm, tc_vec, tc_x1f, tc_win, tc_cnt;     // tensor-core pipeline (wavernn_tc.cuh)
+  bool tc_ok = false;
   int last_push_ncta = 0;
   int* d_grid_error = nullptr;    // set by the grid kernel when a barrier wait timed out (a peer CTA vanished)
   int last_grid_ncta = 0;
@@ -496,6 +499,71 @@ extern "C" int b200tts_wavernn_create(b200tts_wavernn** out, int device, const b
         ctx->pcw.wa = cwd + (size_t)g.ncta * 16 * FEAT;
         ctx->pcw.bias = ctx->pcw.wa + (size_t)g.ncta * 36 * AUX;
         ctx->pcw.ncta = g.ncta; ctx->pcw.feat = FEAT; ctx->pcw.aux = AUX;
+
+        // ---- tensor-core pipeline (wavernn_tc.cuh): per-CTA B-operand images, every weight split into two fp16 planes
+        //      (hi, lo' = (w - hi) * 2048) in the UMMA K-major no-swizzle layout [plane][k-step 32][k half 2][N/8][8 cols][8 halves]
+        if (NC == 1024 && ctx->sm_count >= kTcCtas) {
+          std::vector<uint16_t> img((size_t)kTcCtas * kTcWimgBytes / 2, 0);
+          std::vector<float> prm((size_t)kTcCtas * kTcPrm, 0.f);
+          auto put = [&](uint16_t* base, int N, int col, const float* wrow) {     // one weight row (K = 512) -> column `col` of an image
+            for (int k = 0; k < 512; ++k) {
+              const float w = wrow[k];
+              const __half hi = __float2half_rn(w);
+              const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.0f);
+              const size_t off = ((size_t)(k >> 4) * 2 + ((k >> 3) & 1)) * ((size_t)N * 8) + (size_t)(col >> 3) * 64 + (size_t)(col & 7) * 8 + (k & 7);
+              base[off] = __half_as_ushort(hi);
+              base[(size_t)32 * N * 16 + off] = __half_as_ushort(lo);
+            }
+          };
+          auto unit_blob = [&](int unit) { return &pb[(size_t)(unit >> 2) * pm.blob]; };
+          for (int cta = 0; cta < kTcCtas; ++cta) {
+            uint16_t* wi = &img[(size_t)cta * kTcWimgBytes / 2];
+            float* pr = &prm[(size_t)cta * kTcPrm];
+            if (cta < 32) {                                   // GRU-1: 16 units, columns gate*16 + i
+              for (int i = 0; i < 16; ++i) {
+                const int unit = 16 * cta + i, j = unit & 3;
+                const float* b = unit_blob(unit);
+                for (int gate = 0; gate < 3; ++gate) {
+                  put(wi, 48, gate * 16 + i, b + pm.ohh1 + (size_t)(gate * 4 + j) * R);
+                  pr[64 + gate * 16 + i] = b[pm.obhh1 + gate * 4 + j];
+                }
+                for (int kind = 0; kind < 4; ++kind) pr[kind * 16 + i] = b[pm.oAx + kind * 4 + j];
+              }
+            } else if (cta < 96) {                            // GRU-2: 8 units, W_ih2 image then W_hh2 image, columns gate*8 + i (24-31 zero)
+              const int ci = cta - 32;
+              for (int i = 0; i < 8; ++i) {
+                const int unit = 8 * ci + i, j = unit & 3;
+                const float* b = unit_blob(unit);
+                for (int gate = 0; gate < 3; ++gate) {
+                  put(wi, 32, gate * 8 + i, b + pm.oih2 + (size_t)(gate * 4 + j) * R);
+                  put(wi + 32768, 32, gate * 8 + i, b + pm.ohh2 + (size_t)(gate * 4 + j) * R);
+                  pr[gate * 8 + i] = b[pm.obhh2 + gate * 4 + j];
+                }
+              }
+            } else if (cta < 128) {                           // fc1 / fc2: 32 units
+              const bool first = cta < 112;
+              const int ci = first ? cta - 96 : cta - 112;
+              for (int i = 0; i < 32; ++i) {
+                const int unit = 32 * ci + i, j = unit & 3;
+                const float* b = unit_blob(unit);
+                put(wi, 32, i, b + (first ? pm.ofc1 : pm.ofc2) + (size_t)j * R);
+              }
+            } else {                                          // fc3: 64 classes
+              const int ci = cta - 128;
+              for (int i = 0; i < 64; ++i) {
+                const int cls = 64 * ci + i;
+                const float* b = &pb[(size_t)(cls >> 3) * pm.blob];
+                put(wi, 64, i, b + pm.ofc3 + (size_t)(cls & 7) * F);
+                pr[i] = b[pm.obfc3 + (cls & 7)];
+              }
+            }
+          }
+          ctx->tc_wimg.ensure(img.size() * sizeof(uint16_t));
+          B200_CUDA(cudaMemcpy(ctx->tc_wimg.p, img.data(), img.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+          ctx->tc_prm.ensure(prm.size() * sizeof(float));
+          B200_CUDA(cudaMemcpy(ctx->tc_prm.p, prm.data(), prm.size() * sizeof(float), cudaMemcpyHostToDevice));
+          ctx->tc_ok = true;
+        }
       }
     }
   }
@@ -531,6 +599,7 @@ extern "C" void b200tts_wavernn_destroy(b200tts_wavernn* ctx) {
   ctx->push_vec.release();
   ctx->push_best.release();
   ctx->push_prof.release();
+  ctx->tc_wimg.release(); ctx->tc_prm.release(); ctx->tc_vec.release(); ctx->tc_x1f.release(); ctx->tc_win.release(); ctx->tc_cnt.release();
   ctx->h_stage.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -861,6 +930,59 @@ static void launch_push(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, c
   B200_CUDA(cudaEventRecord(ctx->ev1, st));
 }
 
+// ---- tensor-core pipeline (wavernn_tc.cuh): 33 ... 256 rows, plain batches ----------------------------------------------
+static bool tc_eligible(const b200tts_wavernn* ctx, int rows, bool folding, bool packing) {
+  return ctx->tc_ok && ctx->pm.ok && !folding && !packing && rows >= 1 && rows <= kTcRows * kTcMaxGroups;
+}
+static void launch_tc(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cudaStream_t st) {
+  const b200tts_wavernn_cfg& c = ctx->cfg;
+  const PushModel& pm = ctx->pm;
+  const int rows = ua.B, T = ua.T, hop = c.hop_length;
+  const int ng = (rows + kTcRows - 1) / kTcRows;
+  ctx->push_tab.ensure((size_t)rows * (T + 1) * pm.ncta * kPushCondRows * sizeof(float));
+  {
+    constexpr int FT = 8;
+    dim3 grid((T + 1 + FT - 1) / FT, rows);
+    size_t smem = (size_t)(c.feat_dims + c.res_out_dims) * FT * sizeof(float);
+    push_cond_table_kernel<FT><<<grid, 256, smem, st>>>(ctx->pcw, d_mel, ua.aux_frames, rows, T, ctx->push_tab.as<float>());
+    B200_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  ctx->tc_vec.ensure((size_t)TV_COUNT * ng * 2 * kTcVecBytes);
+  ctx->tc_x1f.ensure((size_t)ng * 2 * kTcRows * 512 * sizeof(float));
+  ctx->tc_win.ensure((size_t)ng * 2 * kTcRows * 16 * sizeof(unsigned long long));
+  const size_t ncnt = (size_t)ng * TCN_COUNT * 32;
+  ctx->tc_cnt.ensure((ncnt + 32) * sizeof(unsigned));
+  B200_CUDA(cudaMemsetAsync(ctx->tc_cnt.p, 0, (ncnt + 32) * sizeof(unsigned), st));
+  int* d_err = reinterpret_cast<int*>(ctx->tc_cnt.as<unsigned>() + ncnt);
+  ctx->d_grid_error = d_err;
+  TcArgs a{};
+  a.wimg = ctx->tc_wimg.as<uint8_t>();
+  a.prm = ctx->tc_prm.as<float>();
+  a.vec = ctx->tc_vec.as<uint8_t>();
+  a.x1f = ctx->tc_x1f.as<float>();
+  a.winners = ctx->tc_win.as<unsigned long long>();
+  a.cnt = ctx->tc_cnt.as<unsigned>();
+  a.error = d_err;
+  a.tab = ctx->push_tab.as<float>();
+  a.fir = ctx->d_fir;
+  a.NT = ctx->NT; a.B = rows; a.S = ua.S; a.T = T; a.hop = hop; a.steps = ua.steps; a.ng = ng; a.NC = ctx->NC;
+  a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.utt_ids = ua.utt_ids; a.q = ua.q;
+  a.teacher = ua.teacher; a.logits_out = ua.logits_out; a.labels = ua.labels;
+  a.prof = nullptr;
+  ctx->last_push_ncta = 0;
+  ctx->last_grid_ncta = 0;
+  B200_CUDA(cudaFuncSetAttribute(wavernn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  int per_sm = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wavernn_tc_kernel, kTcThreads, (size_t)kTcSmemBytes));
+  REQUIRE(per_sm * ctx->sm_count >= kTcCtas, B200TTS_EINVAL, "tensor-core kernel cannot be made co-resident on this device");
+  B200_CUDA(cudaEventRecord(ctx->ev0, st));
+  void* args[] = {(void*)&a};
+  B200_CUDA(cudaLaunchCooperativeKernel((const void*)wavernn_tc_kernel, dim3(kTcCtas), dim3(kTcThreads), args, (size_t)kTcSmemBytes, st));
+  ctx->launches++;
+  B200_CUDA(cudaEventRecord(ctx->ev1, st));
+}
+
 // After the stream has been synchronised: did the last grid launch abandon a barrier?
 static void check_grid_error(b200tts_wavernn* ctx) {
   if (!ctx->d_grid_error) return;
@@ -937,7 +1059,8 @@ static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, i
                       "back to the L2-streaming utterance kernel (about 4x slower at large batch)\n");
     }
   }
-  REQUIRE(kernel == B200TTS_KERNEL_UTTERANCE || kernel == B200TTS_KERNEL_GRID, B200TTS_EINVAL, "unknown kernel selector");
+  REQUIRE(kernel == B200TTS_KERNEL_UTTERANCE || kernel == B200TTS_KERNEL_GRID || kernel == B200TTS_KERNEL_TC, B200TTS_EINVAL,
+          "unknown kernel selector");
   const bool folding = o.fold_target > 0;
   FoldGeom fg{};
   if (folding) {
@@ -963,7 +1086,14 @@ static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, i
     ctx->labels.ensure((size_t)GB * GS * sizeof(int16_t));
     labels = ctx->labels.as<int16_t>();
   }
-  const bool use_push = kernel == B200TTS_KERNEL_GRID && push_eligible(ctx, packing ? o.pack_rows : GB);
+  bool use_tc = false;
+  if (kernel == B200TTS_KERNEL_TC) {
+    REQUIRE(tc_eligible(ctx, GB, folding, packing), B200TTS_EINVAL,
+            "kernel=tc needs rnn_dims = fc_dims = 512, 10-bit classes, >= 144 SMs, 1..256 rows, no folding / packing");
+    use_tc = true;
+    kernel = B200TTS_KERNEL_GRID;
+  }
+  const bool use_push = !use_tc && kernel == B200TTS_KERNEL_GRID && push_eligible(ctx, packing ? o.pack_rows : GB);
   REQUIRE(!packing || use_push, B200TTS_EINVAL, "packed generation needs the push kernel (kernel=auto/grid, rnn_dims = fc_dims = 512)");
   if (kernel == B200TTS_KERNEL_GRID && !ctx->gm.ok)
     throw Error(B200TTS_EINVAL, "kernel=grid was requested but this model/device cannot run the weight-stationary grid kernel "
@@ -1006,6 +1136,8 @@ static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, i
     else if (per <= 4) launch_utt<4>(ctx, a, st);
     else launch_utt<8>(ctx, a, st);
     B200_CUDA(cudaEventRecord(ctx->ev1, st));
+  } else if (use_tc) {
+    launch_tc(ctx, d_mel, a, st);
   } else if (use_push) {
     PackInfo pi{o.d_pack_utt, o.d_pack_start, o.pack_rows, o.pack_segs, o.pack_steps, B};
     launch_push(ctx, d_mel, a, st, folding ? &fg : nullptr, T, packing ? &pi : nullptr);

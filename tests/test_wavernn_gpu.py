@@ -328,8 +328,23 @@ def _distinct_cond(p, B, T, seed, distinct=16):
     return tile(mels), (tile(up), tile(aux))
 
 
+# the tensor-core pipeline (wavernn_tc.cuh, kernel='tc'): two full groups, a partial second group, one group, a partial group
+TC_BATCHES = [256, 200, 128, 100, 40]
+
+
+@pytest.mark.parametrize('B', TC_BATCHES)
+def test_tc_teacher_forced_logits_vs_oracle(torch_cuda, B):
+    """The split-fp16 tcgen05 kernel to the SAME bar as the fp32 CUDA-core mappings: all rows, 300 steps, shipped checkpoint."""
+    test_mapping_teacher_forced_logits_vs_oracle(torch_cuda, B, kernel='tc')
+
+
+@pytest.mark.parametrize('B', TC_BATCHES)
+def test_tc_free_running_labels_vs_oracle(torch_cuda, B):
+    test_mapping_free_running_labels_vs_oracle(torch_cuda, B, kernel='tc')
+
+
 @pytest.mark.parametrize('B', MAPPING_BATCHES)
-def test_mapping_teacher_forced_logits_vs_oracle(torch_cuda, B):
+def test_mapping_teacher_forced_logits_vs_oracle(torch_cuda, B, kernel='grid'):
     """Teacher-forced logits of ALL rows for 300 steps, shipped checkpoint, every mapping, against oracle.generate.
     Same bar as the golden tests: 5e-6 * max|logit| + 1e-4."""
     eng, p = engine_for('ckpt')
@@ -338,7 +353,7 @@ def test_mapping_teacher_forced_logits_vs_oracle(torch_cuda, B):
     mels, cond = _distinct_cond(p, B, T, 4000 + B)
     teacher = np.random.RandomState(B).randint(0, 1024, size=(B, S)).astype(np.int16)
     ref = wo.generate(p, mels, teacher=teacher, keep_logits='all', max_steps=steps, cond=cond)
-    out = eng.generate(mels, seed=B, teacher=teacher, return_logits=True, max_steps=steps, kernel='grid')
+    out = eng.generate(mels, seed=B, teacher=teacher, return_logits=True, max_steps=steps, kernel=kernel)
     lg = out['logits'].cpu().numpy()
     want = np.stack([ref['logits'][s] for s in range(steps)])
     scale = max(1.0, float(np.abs(want).max()))
@@ -349,7 +364,7 @@ def test_mapping_teacher_forced_logits_vs_oracle(torch_cuda, B):
 
 
 @pytest.mark.parametrize('B', MAPPING_BATCHES)
-def test_mapping_free_running_labels_vs_oracle(torch_cuda, B):
+def test_mapping_free_running_labels_vs_oracle(torch_cuda, B, kernel='grid'):
     """Free-running labels for 2000 steps under the production Philox noise, shipped checkpoint: >= 16 rows spread over
     both utterance groups and every tile position must reproduce the oracle's sequence (the Philox stream of each row is
     dumped and replayed through the oracle); a first mismatch is accepted only as a sampling near-tie."""
@@ -358,7 +373,7 @@ def test_mapping_free_running_labels_vs_oracle(torch_cuda, B):
     mels, cond = _distinct_cond(p, B, T, 5000 + B)
     rows = sorted(set([0, B - 1, B // 2, max(0, B // 2 - 1)] + [int(r) for r in np.linspace(0, B - 1, 16)]
                       + [r for r in (31, 32, 127, 128, 129, 255, 256, 299) if r < B]))
-    out = eng.generate(mels, seed=seed, max_steps=steps, kernel='grid')
+    out = eng.generate(mels, seed=seed, max_steps=steps, kernel=kernel)
     lab = out['labels'].cpu().numpy()[:, :steps]
     q = np.concatenate([eng.philox_exponential(seed, r, 1, 0, steps).cpu().numpy() for r in rows], axis=1)
     sub = (cond[0][rows], cond[1][rows])
