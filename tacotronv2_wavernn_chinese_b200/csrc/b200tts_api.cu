@@ -161,7 +161,7 @@ struct b200tts_wavernn {
   PushModel pm{};                 // small-batch push kernel (wavernn_push.cuh): per-CTA blobs + conditioning-projection weights
   PushCondW pcw{};
   DeviceBuf push_blob, push_condw, push_tab, push_vec, push_best, push_prof;
-  DeviceBuf tc_wimg, tc_prm, tc_vec, tc_x1f, tc_win, tc_cnt;     // tensor-core pipeline (wavernn_tc.cuh)
+  DeviceBuf tc_wimg, tc_prm, tc_vec, tc_x1f, tc_win, tc_cnt, tc_cond;     // tensor-core pipeline (wavernn_tc.cuh)
   bool tc_ok = false;
   int last_push_ncta = 0;
   int* d_grid_error = nullptr;    // set by the grid kernel when a barrier wait timed out (a peer CTA vanished)
@@ -599,7 +599,7 @@ extern "C" void b200tts_wavernn_destroy(b200tts_wavernn* ctx) {
   ctx->push_vec.release();
   ctx->push_best.release();
   ctx->push_prof.release();
-  ctx->tc_wimg.release(); ctx->tc_prm.release(); ctx->tc_vec.release(); ctx->tc_x1f.release(); ctx->tc_win.release(); ctx->tc_cnt.release();
+  ctx->tc_wimg.release(); ctx->tc_prm.release(); ctx->tc_vec.release(); ctx->tc_x1f.release(); ctx->tc_win.release(); ctx->tc_cnt.release(); ctx->tc_cond.release();
   ctx->h_stage.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -951,6 +951,8 @@ static void launch_tc(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cud
   ctx->tc_vec.ensure((size_t)TV_COUNT * ng * 2 * kTcVecBytes);
   ctx->tc_x1f.ensure((size_t)ng * 2 * kTcRows * 512 * sizeof(float));
   ctx->tc_win.ensure((size_t)ng * 2 * kTcRows * 16 * sizeof(unsigned long long));
+  ctx->tc_cond.ensure((size_t)32 * 2 * ng * kTcCondBlk * kTcCondSlot * sizeof(float));
+  REQUIRE((size_t)hop * ctx->NT * sizeof(float) <= (size_t)kTcFirMaxBytes, B200TTS_EINVAL, "tensor-core kernel: FIR table does not fit its shared-memory slot");
   const size_t ncnt = (size_t)ng * TCN_COUNT * 32;
   ctx->tc_cnt.ensure((ncnt + 32) * sizeof(unsigned));
   B200_CUDA(cudaMemsetAsync(ctx->tc_cnt.p, 0, (ncnt + 32) * sizeof(unsigned), st));
@@ -963,6 +965,7 @@ static void launch_tc(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cud
   a.x1f = ctx->tc_x1f.as<float>();
   a.winners = ctx->tc_win.as<unsigned long long>();
   a.cnt = ctx->tc_cnt.as<unsigned>();
+  a.condg = ctx->tc_cond.as<float>();
   a.error = d_err;
   a.tab = ctx->push_tab.as<float>();
   a.fir = ctx->d_fir;
@@ -970,6 +973,12 @@ static void launch_tc(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cud
   a.rng_mode = ua.rng_mode; a.seed = ua.seed; a.utt_offset = ua.utt_offset; a.utt_ids = ua.utt_ids; a.q = ua.q;
   a.teacher = ua.teacher; a.logits_out = ua.logits_out; a.labels = ua.labels;
   a.prof = nullptr;
+  const bool prof = getenv("B200TTS_TC_PROF") != nullptr;
+  if (prof) {
+    ctx->push_prof.ensure((size_t)kTcCtas * 12 * sizeof(long long));
+    B200_CUDA(cudaMemsetAsync(ctx->push_prof.p, 0, (size_t)kTcCtas * 12 * sizeof(long long), st));
+    a.prof = ctx->push_prof.as<long long>();
+  }
   ctx->last_push_ncta = 0;
   ctx->last_grid_ncta = 0;
   B200_CUDA(cudaFuncSetAttribute(wavernn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
@@ -981,6 +990,24 @@ static void launch_tc(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cud
   B200_CUDA(cudaLaunchCooperativeKernel((const void*)wavernn_tc_kernel, dim3(kTcCtas), dim3(kTcThreads), args, (size_t)kTcSmemBytes, st));
   ctx->launches++;
   B200_CUDA(cudaEventRecord(ctx->ev1, st));
+  if (prof) {      // development aid: mean cycles per lock-step and role, to stderr
+    B200_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> h((size_t)kTcCtas * 12);
+    B200_CUDA(cudaMemcpy(h.data(), ctx->push_prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    static const char* names[12] = {"ld:cnt", "ld:empty+issue", "mma:accfree", "mma:full", "mma:issue", "epi:wait-main", "epi:wait-other",
+                                    "epi:tmem", "epi:math+store", "epi:publish", "cond:wait", "cond:compute"};
+    static const char* roles[5] = {"GRU1", "GRU2", "fc1", "fc2", "fc3"};
+    const int lo[6] = {0, 32, 96, 112, 128, 144};
+    for (int r = 0; r < 5; ++r) {
+      fprintf(stderr, "tc prof %-4s (cycles per lock-step):", roles[r]);
+      for (int i = 0; i < 12; ++i) {
+        double s = 0;
+        for (int cta = lo[r]; cta < lo[r + 1]; ++cta) s += (double)h[(size_t)cta * 12 + i];
+        fprintf(stderr, " %s=%.0f", names[i], s / (lo[r + 1] - lo[r]) / ua.steps);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
 }
 
 // After the stream has been synchronised: did the last grid launch abandon a barrier?
