@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
     // not leave the others of its warp behind in a .sync.aligned instruction).
     auto publish = [&](int g, int which) {
       TC_MARK(8);
-      asm volatile("fence.proxy.async;" ::: "memory");
+      // (the generic -> async proxy fence of this exchange is executed by the CONSUMER's loader thread, after its acquire)
       if (__any_sync(0xffffffffu, pg.aborted)) { pg.aborted = true; return; }
       if (lane == 0) tc_red_release(counter(g, which), 1u);
       TC_MARK(9);
@@ -448,11 +448,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
     if (R.role == TC_ROLE_G1) {
       constexpr int U = 16 / kTcEW;                        // units per thread
       const int u0 = U * sub;
-      float h1own[kTcMaxGroups][U];
+      float h1own[kTcMaxGroups][U], ghs[kTcMaxGroups][3][U];   // ghs: W_hh1 . h1(t-1) of this thread's units (0 at t = 0)
 #pragma unroll
       for (int g = 0; g < kTcMaxGroups; ++g)
 #pragma unroll
-        for (int i = 0; i < U; ++i) h1own[g][i] = 0.f;
+        for (int i = 0; i < U; ++i) { h1own[g][i] = 0.f; ghs[g][0][i] = 0.f; ghs[g][1][i] = 0.f; ghs[g][2][i] = 0.f; }
       const float* Ax = prm;                               // [4 kinds][16]
       const float* bhh = prm + 64;                         // [3 gates][16]
       int blk_t0 = 0, blk_t1 = 0, blk_i = -1;               // current conditioning block: steps [blk_t0, blk_t1) of all groups
@@ -501,21 +501,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
             }
           }
           if (t == A.steps) continue;                      // the extra trip only collects the last winner
-          // W_hh1 . h1(t-1) of this row: columns gate*16 + unit, waiting in TMEM slot g since the previous step
-          float gh[3][U];
-          if (t > 0) {
-            acc_wait(g);
-            const uint32_t ts = tlane + (uint32_t)(g * 240);
-#pragma unroll
-            for (int gate = 0; gate < 3; ++gate) tc_readW<48, U>(ts, gate * 16 + u0, gh[gate]);
-            acc_release(g);
-            TC_MARK(7);
-          } else {
-#pragma unroll
-            for (int gate = 0; gate < 3; ++gate)
-#pragma unroll
-              for (int i = 0; i < U; ++i) gh[gate][i] = 0.f;
-          }
           float hnew[U], x1[U];
 #pragma unroll
           for (int i = 0; i < U; ++i) {
@@ -523,8 +508,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
             const float gir = fmaf(Ax[16 + u0 + i], x, cd[1][i]);
             const float giz = fmaf(Ax[32 + u0 + i], x, cd[2][i]);
             const float gin = fmaf(Ax[48 + u0 + i], x, cd[3][i]);
-            const float h = gru_update(gir, giz, gin, gh[0][i] + bhh[u0 + i], gh[1][i] + bhh[16 + u0 + i], gh[2][i] + bhh[32 + u0 + i],
-                                       h1own[g][i]);
+            const float h = gru_update(gir, giz, gin, ghs[g][0][i] + bhh[u0 + i], ghs[g][1][i] + bhh[16 + u0 + i],
+                                       ghs[g][2][i] + bhh[32 + u0 + i], h1own[g][i]);
             h1own[g][i] = h;
             hnew[i] = h;
             x1[i] = iout + h;
@@ -535,6 +520,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
 #pragma unroll
           for (int i = 0; i < U; i += 4) *reinterpret_cast<float4*>(xf + i) = make_float4(x1[i], x1[i + 1], x1[i + 2], x1[i + 3]);
           publish(g, TCN_C1);
+          // off the critical path: W_hh1 . h1(t) (the GEMM all GRU-1 CTAs start once h1(t) is complete) is moved from TMEM to
+          // registers as soon as it is done, so that the gate math of step t+1 finds it there
+          acc_wait(g);
+          {
+            const uint32_t ts = tlane + (uint32_t)(g * 240);
+#pragma unroll
+            for (int gate = 0; gate < 3; ++gate) tc_readW<48, U>(ts, gate * 16 + u0, ghs[g][gate]);
+          }
+          acc_release(g);
+          TC_MARK(7);
         }
         if (t < A.steps && t == blk_t1 - 1) {                // the block's values are all in registers / used: one arrival per warp
           __syncwarp();
@@ -545,11 +540,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
       constexpr int U = 8 / kTcEW;                         // 2 units per thread
       static_assert(U == 2, "GRU-2 epilogue is written for 2 units per thread");
       const int u0 = U * sub;
-      float h2own[kTcMaxGroups][U];
+      float h2own[kTcMaxGroups][U], ghs[kTcMaxGroups][3][U];
 #pragma unroll
       for (int g = 0; g < kTcMaxGroups; ++g)
 #pragma unroll
-        for (int i = 0; i < U; ++i) h2own[g][i] = 0.f;
+        for (int i = 0; i < U; ++i) { h2own[g][i] = 0.f; ghs[g][0][i] = 0.f; ghs[g][1][i] = 0.f; ghs[g][2][i] = 0.f; }
       const float* bhh = prm;                              // [3 gates][8]
       for (int t = 0; t < A.steps && !pg.aborted; ++t) {
         const int fr = t / A.hop;
@@ -567,7 +562,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
               cd[gate][0] = v.x; cd[gate][1] = v.y;
             }
           }
-          float gi[3][U], gh[3][U];
+          float gi[3][U];
           TC_MARK(8);
           acc_wait(2);
           TC_MARK(5);
@@ -575,19 +570,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           for (int gate = 0; gate < 3; ++gate) tc_readW<32, U>(tlane + 320u, gate * 8 + u0, gi[gate]);
           acc_release(2);
           TC_MARK(7);
-          if (t > 0) {
-            acc_wait(g);
-            TC_MARK(6);
-#pragma unroll
-            for (int gate = 0; gate < 3; ++gate) tc_readW<32, U>(tlane + (uint32_t)(g * 160), gate * 8 + u0, gh[gate]);
-            acc_release(g);
-            TC_MARK(7);
-          } else {
-#pragma unroll
-            for (int gate = 0; gate < 3; ++gate)
-#pragma unroll
-              for (int i = 0; i < U; ++i) gh[gate][i] = 0.f;
-          }
           // own units of x1 (fp32): the loader's acquire made x1 visible to the bulk copies; this thread needs its own
           tc_cnt_wait(counter(g, TCN_C1), (unsigned)(32 * 4 * kTcEW) * (unsigned)(t + 1), pg);
           TC_MARK(6);
@@ -596,8 +578,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           float hnew[U], x2[U];
 #pragma unroll
           for (int i = 0; i < U; ++i) {
-            const float h = gru_update(gi[0][i] + cd[0][i], gi[1][i] + cd[1][i], gi[2][i] + cd[2][i], gh[0][i] + bhh[u0 + i],
-                                       gh[1][i] + bhh[8 + u0 + i], gh[2][i] + bhh[16 + u0 + i], h2own[g][i]);
+            const float h = gru_update(gi[0][i] + cd[0][i], gi[1][i] + cd[1][i], gi[2][i] + cd[2][i], ghs[g][0][i] + bhh[u0 + i],
+                                       ghs[g][1][i] + bhh[8 + u0 + i], ghs[g][2][i] + bhh[16 + u0 + i], h2own[g][i]);
             h2own[g][i] = h;
             hnew[i] = h;
             x2[i] = x1[i] + h;
@@ -605,6 +587,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           tc_storeW<U>(vec_img(TV_H2, g, t & 1), 8 * R.ci + u0, row, hnew);
           tc_storeW<U>(vec_img(TV_X2, g, t & 1), 8 * R.ci + u0, row, x2);
           publish(g, TCN_C2);
+          // off the critical path: W_hh2 . h2(t) from TMEM to registers for step t+1
+          acc_wait(g);
+          TC_MARK(6);
+#pragma unroll
+          for (int gate = 0; gate < 3; ++gate) tc_readW<32, U>(tlane + (uint32_t)(g * 160), gate * 8 + u0, ghs[g][gate]);
+          acc_release(g);
+          TC_MARK(7);
         }
       }
     } else if (R.role == TC_ROLE_F1 || R.role == TC_ROLE_F2) {
