@@ -48,7 +48,7 @@ def parse():
     ap.add_argument('--impl', choices=('b200', 'reference'), default='b200')
     ap.add_argument('--batch', type=int, default=256, help='utterances per GPU (weak line) = global batch of the strong line')
     ap.add_argument('--frames', type=int, default=80)
-    ap.add_argument('--kernel', default='auto', choices=('auto', 'grid', 'utterance'))
+    ap.add_argument('--kernel', default='auto', choices=('auto', 'grid', 'utterance', 'tc'))
     ap.add_argument('--weights', default='auto', choices=('auto', 'shipped', 'synthetic'))
     ap.add_argument('--workload', default='config3', choices=('config3', 'text2audio', 'tacotron'),
                     help='config3 (default, the BASELINE metric) | text2audio: BASELINE config 5, 64 sentences text->mel->audio sharded '
@@ -528,11 +528,13 @@ def main():
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if N > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        measure.kernel = eng.last_kernel()
         return float(t.item()), float(np.mean(kms)), int(launches)
 
     sampler = ClockSampler(local)
     sampler.start()
     ms, gen_ms, launches = measure(B, rank * B, args.steps, args.warmup)
+    weak_kernel = measure.kernel
     clocks = sampler.stop()
     value = N * B * S * args.steps / (ms / 1e3)
 
@@ -592,6 +594,18 @@ def main():
         except Exception:
             pass
         fpeak = fp32_measured or nominal_fp32
+        # tensor-core pipeline (wavernn_tc_kernel): every fp32 operand is two fp16 planes and a dot product is three kind::f16
+        # MMA products, so the tensor cores EXECUTE 3x the algorithmic GEMM work (6656 x 512 MAC per sample; the conditioning
+        # and the fed-back sample column stay on the CUDA cores).  The kernel is bound by the latency of its five-exchange
+        # dependency chain, not by either ceiling; both forms are reported.
+        tensor_form = None
+        if weak_kernel == 'wavernn_tc_kernel':
+            tf = 3 * 2 * 6656 * 512 * B * S / (gen_ms / 1e3) / 1e12
+            tpeak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1437.7)))
+            tensor_form = {'executed': tf, 'peak': tpeak, 'unit': 'TFLOP/s (kind::f16 tcgen05.mma, fp32 accumulate)', 'frac': tf / tpeak,
+                           'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if 'bf16_tflops_sustained' in peaks
+                           else 'fallback', 'products_per_dot': 3,
+                           'note': 'latency-bound pipeline: 2 groups of 128 rows in flight over 144 layer-stationary CTAs'}
         line = {
             'metric': 'wavernn_audio_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': N,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -602,9 +616,10 @@ def main():
             'us_per_lockstep': 1e3 * gen_ms / S,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
                          'traffic': traffic, 'traffic_captured_on': traffic_note, 'peak_source': peak_src,
-                         'note': 'weights are SMEM-stationary, so the HBM form is small by construction; the binding '
-                                 'resources are fp32 FMA issue and the L2->SM broadcast of the activations (see flop_form)',
-                         'kernel_ms': gen_ms, 'algorithmic_bytes_per_launch': alg_bytes,
+                         'note': 'weights are SMEM-stationary, so the HBM form is small by construction; the binding resources are '
+                                 'fp32 FMA issue + the L2->SM broadcast of the activations (wide CUDA-core mapping) or the latency of '
+                                 'the per-step exchange chain (tensor-core pipeline); see flop_form / tensor_form',
+                         'kernel': weak_kernel, 'kernel_ms': gen_ms, 'algorithmic_bytes_per_launch': alg_bytes, 'tensor_form': tensor_form,
                          'flop_form': {'achieved': flops, 'peak': fpeak, 'unit': 'TFLOP/s fp32 CUDA-core',
                                        'frac': flops / fpeak,
                                        'peak_source': 'measured: register-only FFMA2 loop on all SMs (b200tts_debug_fp32_peak)'

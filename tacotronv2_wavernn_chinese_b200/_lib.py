@@ -75,6 +75,7 @@ SIGNATURES = {
                                              C.c_void_p, C.c_void_p]),
     'b200tts_wavernn_launch_count': (C.c_int64, [C.c_void_p]),
     'b200tts_wavernn_last_kernel_ms': (C.c_double, [C.c_void_p]),
+    'b200tts_wavernn_last_kernel': (C.c_int, [C.c_void_p]),
     'b200tts_wavernn_debug_phase_cycles': (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     'b200tts_wavernn_check': (C.c_int, [C.c_void_p]),
     'b200tts_debug_fp32_peak': (C.c_int, [C.c_int, C.POINTER(C.c_double)]),

@@ -163,6 +163,7 @@ struct b200tts_wavernn {
   DeviceBuf push_blob, push_condw, push_tab, push_vec, push_best, push_prof;
   DeviceBuf tc_wimg, tc_prm, tc_vec, tc_x1f, tc_win, tc_cnt, tc_cond;     // tensor-core pipeline (wavernn_tc.cuh)
   bool tc_ok = false;
+  int last_kernel = 0;            // 1 utterance, 2 wide grid, 3 push, 4 multi-group push, 5 tensor-core pipeline
   int last_push_ncta = 0;
   int* d_grid_error = nullptr;    // set by the grid kernel when a barrier wait timed out (a peer CTA vanished)
   int last_grid_ncta = 0;
@@ -608,6 +609,8 @@ extern "C" void b200tts_wavernn_destroy(b200tts_wavernn* ctx) {
 }
 
 extern "C" int64_t b200tts_wavernn_launch_count(const b200tts_wavernn* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int b200tts_wavernn_last_kernel(const b200tts_wavernn* ctx) { return ctx ? ctx->last_kernel : 0; }
 
 extern "C" double b200tts_wavernn_last_kernel_ms(b200tts_wavernn* ctx) {
   if (!ctx || !ctx->ev_valid) {
@@ -1114,6 +1117,13 @@ static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, i
     labels = ctx->labels.as<int16_t>();
   }
   bool use_tc = false;
+  // kernel=auto: the tensor-core pipeline costs ~50 us per lock-step whatever the row count (1 or 2 groups of 128 rows in flight),
+  // the wide CUDA-core mapping 33.8 / 41.4 / 68.0 us at 64 / 128 / 256 rows -> the crossover is near 160 rows (env
+  // B200TTS_TC_MIN_ROWS; B200TTS_TC=0 keeps the CUDA-core mappings).  Fold mode and packed rows stay on the other kernels.
+  static const int tc_min_rows = getenv("B200TTS_TC_MIN_ROWS") ? atoi(getenv("B200TTS_TC_MIN_ROWS")) : 161;
+  static const bool tc_off = getenv("B200TTS_TC") != nullptr && getenv("B200TTS_TC")[0] == '0';
+  if (o.kernel == B200TTS_KERNEL_AUTO && kernel == B200TTS_KERNEL_GRID && !tc_off && GB >= tc_min_rows && tc_eligible(ctx, GB, folding, packing))
+    kernel = B200TTS_KERNEL_TC;
   if (kernel == B200TTS_KERNEL_TC) {
     REQUIRE(tc_eligible(ctx, GB, folding, packing), B200TTS_EINVAL,
             "kernel=tc needs rnn_dims = fc_dims = 512, 10-bit classes, >= 144 SMs, 1..256 rows, no folding / packing");
@@ -1141,6 +1151,7 @@ static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, i
   REQUIRE(!(folding && r.d_utterance_ids), B200TTS_EINVAL, "d_utterance_ids cannot be combined with fold-with-overlap generation");
   a.teacher = o.d_teacher; a.logits_out = o.d_logits; a.labels = labels;
 
+  ctx->last_kernel = kernel == B200TTS_KERNEL_UTTERANCE ? 1 : (use_tc ? 5 : (use_push ? (GB > kMgG && !packing ? 4 : 3) : 2));
   if (kernel == B200TTS_KERNEL_UTTERANCE) {
     if (folding) {   // per-fold conditioning in the row-major layout this kernel reads, aux per sample (hop = 1)
       ctx->fold_mels.ensure((size_t)GB * GS * c.feat_dims * sizeof(float));

@@ -426,8 +426,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
     // One arrival per WARP: its 32 rows are stored -> lane 0 releases (red.release.gpu is cumulative over what the warp barrier
     // ordered before it).  No block barrier on the critical path; the warp also agrees on giving up (a lane that timed out must
     // not leave the others of its warp behind in a .sync.aligned instruction).
-    auto publish = [&](int g, int which) {
-      TC_MARK(8);
+    auto publish = [&](int g, int which, bool mark = true) {
+      if (mark) TC_MARK(8);
       // (the generic -> async proxy fence of this exchange is executed by the CONSUMER's loader thread, after its acquire)
       if (__any_sync(0xffffffffu, pg.aborted)) { pg.aborted = true; return; }
       if (lane == 0) tc_red_release(counter(g, which), 1u);
@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
             }
           }
           if (t == A.steps) continue;                      // the extra trip only collects the last winner
+          TC_MARK(6);
           float hnew[U], x1[U];
 #pragma unroll
           for (int i = 0; i < U; ++i) {
@@ -514,12 +515,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
             hnew[i] = h;
             x1[i] = iout + h;
           }
+          TC_MARK(8);
           tc_storeW<U>(vec_img(TV_H1, g, t & 1), 16 * R.ci + u0, row, hnew);
           tc_storeW<U>(vec_img(TV_X1, g, t & 1), 16 * R.ci + u0, row, x1);
           float* xf = A.x1f + (((size_t)g * 2 + (t & 1)) * kTcRows + row) * 512 + 16 * R.ci + u0;
 #pragma unroll
           for (int i = 0; i < U; i += 4) *reinterpret_cast<float4*>(xf + i) = make_float4(x1[i], x1[i + 1], x1[i + 2], x1[i + 3]);
-          publish(g, TCN_C1);
+          publish(g, TCN_C1, false);
           // off the critical path: W_hh1 . h1(t) (the GEMM all GRU-1 CTAs start once h1(t) is complete) is moved from TMEM to
           // registers as soon as it is done, so that the gate math of step t+1 finds it there
           acc_wait(g);
