@@ -47,6 +47,7 @@ constexpr int kTcVecBytes = kTcStagesPerVec * kTcStageBytes;
 constexpr int kTcCtas = 144;
 constexpr int kTcWimgBytes = 131072;        // per-CTA weight image slot
 constexpr int kTcPrm = 128;                 // per-CTA fp32 parameters
+constexpr int kTcWinCopies = 8;              // the winner words are written 8 times: 32 GRU-1 CTAs x 512 threads read them at the same moment
 constexpr int kTcCondBlk = 8;               // GRU-1 conditioning is produced in blocks of <= 8 consecutive steps of one frame
 constexpr int kTcCondSlot = kTcRows * 64;   // floats of one (step, group) of the conditioning ring
 constexpr int kTcSmemBytes = 131072 + 6 * kTcStageBytes + kTcPrm * 4;   // the GRU-2 / fc3 CTAs' need (largest); GRU-1: 96 KB + 6 stages + FIR
@@ -60,7 +61,7 @@ struct TcArgs {
   const float* prm;              // [144][128]
   uint8_t* vec;                  // [TV_COUNT][ng][2][kTcVecBytes]
   float* x1f;                    // [ng][2][128][512] fp32 copy of x1 (GRU-2 CTAs add their h2 to it: x2 = x1 + h2)
-  unsigned long long* winners;   // [ng][2][128][16]
+  unsigned long long* winners;   // [ng][2][kTcWinCopies][128][16]
   unsigned* cnt;                 // [ng][TCN_COUNT][32] arrival counters (one 128-byte line each, one arrival per epilogue WARP), zeroed before the launch
   float* condg;                  // [32 GRU-1 CTAs][2 block buffers][ng][kTcCondBlk][128 rows][64] conditioning ring (stays in L2)
   int* error;
@@ -110,6 +111,16 @@ __device__ __forceinline__ bool tc_cnt_wait(const unsigned* p, unsigned need, Po
     if (tc_ld_acquire(p) >= need) return true;
     if (pg.expired()) return false;
   }
+}
+// the same for a whole (converged) warp: lane 0 polls, the warp barrier passes the acquired view on -- 32x fewer requests on
+// the counter's L2 line (tens of thousands of threads wait on the same few lines at the same moment)
+__device__ __forceinline__ bool tc_cnt_wait_warp(const unsigned* p, unsigned need, PollGuard& pg, int lane) {
+  bool ok = true;
+  if (lane == 0) ok = tc_cnt_wait(p, need, pg);
+  ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+  __syncwarp();                             // memory ordering among the lanes: they read (ld.cg) what lane 0 acquired
+  if (!ok) pg.aborted = true;
+  return ok;
 }
 // K-major, no swizzle: core matrix = 8 rows x 16 bytes; LBO = stride between the two K halves of one MMA, SBO = stride
 // between 8-row groups (cute/arch/mma_sm100_desc.hpp; same form as tools/umma_split_bench.cu, verified on the GPU)
@@ -483,9 +494,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           }
           float x = 0.f;
           if (t > 0) {
-            tc_cnt_wait(counter(g, TCN_W), 64u * (unsigned)t, pg);
+            tc_cnt_wait_warp(counter(g, TCN_W), 64u * (unsigned)t, pg, lane);
             TC_MARK(5);
-            const unsigned long long* wp = A.winners + (((size_t)g * 2 + ((t - 1) & 1)) * kTcRows + row) * 16;
+            const unsigned long long* wp = A.winners + ((((size_t)g * 2 + ((t - 1) & 1)) * kTcWinCopies + (R.ci & (kTcWinCopies - 1))) * kTcRows + row) * 16;
             unsigned long long best = 0ull;
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
@@ -573,7 +584,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           acc_release(2);
           TC_MARK(7);
           // own units of x1 (fp32): the loader's acquire made x1 visible to the bulk copies; this thread needs its own
-          tc_cnt_wait(counter(g, TCN_C1), (unsigned)(32 * 4 * kTcEW) * (unsigned)(t + 1), pg);
+          tc_cnt_wait_warp(counter(g, TCN_C1), (unsigned)(32 * 4 * kTcEW) * (unsigned)(t + 1), pg, lane);
           TC_MARK(6);
           const float2 xa = __ldcg(reinterpret_cast<const float2*>(A.x1f + (((size_t)g * 2 + (t & 1)) * kTcRows + row) * 512 + 8 * R.ci + u0));
           const float x1[U] = {xa.x, xa.y};
@@ -695,7 +706,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
               const unsigned long long o = swin[k * kTcRows + row];
               best = o > best ? o : best;
             }
-            A.winners[(((size_t)g * 2 + (t & 1)) * kTcRows + row) * 16 + R.ci] = best;
+#pragma unroll
+            for (int cp = 0; cp < kTcWinCopies; ++cp)
+              A.winners[((((size_t)g * 2 + (t & 1)) * kTcWinCopies + cp) * kTcRows + row) * 16 + R.ci] = best;
             publish(g, TCN_W);
           }
           // (swin is rewritten only after the next accumulator wait, which follows this barrier in every thread's program order;
