@@ -1028,21 +1028,27 @@ static void run_generate_rows(b200tts_wavernn* ctx, const float* d_mel, int B, i
 // utterances x large batches would run out of memory before anything else.  Such a call is cut into row ranges whose buffers stay
 // under a budget (default 8 GB, env B200TTS_MAX_COND_BYTES); the noise is keyed by the global row, so the result is unchanged.
 // (Not for the debug modes whose buffers are indexed [step][row]: external noise, logits.)
+static bool tc_eligible(const b200tts_wavernn* ctx, int rows, bool folding, bool packing);
 static void run_generate(b200tts_wavernn* ctx, const float* d_mel, int B, int T, const b200tts_rng* rng,
                          const b200tts_gen_opts* opts, int16_t* d_labels, double* d_wave, cudaStream_t st) {
   const double budget = getenv("B200TTS_MAX_COND_BYTES") ? atof(getenv("B200TTS_MAX_COND_BYTES")) : 8e9;   // read per call
   const b200tts_wavernn_cfg& c = ctx->cfg;
   const double per_row = (double)T * c.hop_length * c.feat_dims * sizeof(float);
-  const bool sliceable = B > 256 || per_row * 256 > budget;
   const bool debug_bufs = (rng && rng->mode == B200TTS_RNG_EXT_EXPONENTIAL) || (opts && opts->d_logits);
   const bool folding = opts && opts->fold_target > 0;
   const bool packing = opts && opts->d_pack_utt;
-  if (!sliceable || debug_bufs || folding || packing || per_row * ((B + 255) / 256 * 256) <= budget || !d_labels) {
+  // kernel=auto and more than 256 rows: launches of 256 rows through the tensor-core pipeline (50 us per lock-step each) beat the
+  // wide mapping on the whole batch (68 us per 256 rows); the noise is keyed by the global row, so the result does not change
+  const bool tc_off = getenv("B200TTS_TC") != nullptr && getenv("B200TTS_TC")[0] == '0';
+  const bool tc_slices = B > kTcRows * kTcMaxGroups && !tc_off && (!opts || opts->kernel == B200TTS_KERNEL_AUTO) && !debug_bufs && d_labels &&
+                         tc_eligible(ctx, kTcRows * kTcMaxGroups, folding, packing);
+  const bool sliceable = tc_slices || B > 256 || per_row * 256 > budget;
+  if (!sliceable || debug_bufs || folding || packing || (!tc_slices && per_row * ((B + 255) / 256 * 256) <= budget) || !d_labels) {
     run_generate_rows(ctx, d_mel, B, T, rng, opts, d_labels, d_wave, st);
     return;
   }
-  int rows = (int)(budget / per_row);
-  rows = rows >= 256 ? rows / 256 * 256 : (rows >= 32 ? 32 : std::max(rows, 1));
+  int rows = tc_slices ? kTcRows * kTcMaxGroups : (int)(budget / per_row);
+  if (!tc_slices) rows = rows >= 256 ? rows / 256 * 256 : (rows >= 32 ? 32 : std::max(rows, 1));
   const size_t S = (size_t)T * c.hop_length, wave_len = (size_t)(T - 1) * c.hop_length;
   for (int r0 = 0; r0 < B; r0 += rows) {
     const int nb = std::min(rows, B - r0);

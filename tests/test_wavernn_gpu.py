@@ -450,6 +450,29 @@ def test_large_request_is_cut_into_row_ranges(torch_cuda):
         np.testing.assert_array_equal(part['wave'].cpu().numpy(), wave[lo:hi])
 
 
+def test_auto_dispatch_and_slicing_through_the_tensor_core_kernel(torch_cuda):
+    """kernel='auto': 161-256 rows run wavernn_tc_kernel; more than 256 rows are cut into launches of 256 rows (tensor-core pipeline)
+    plus a tail on the CUDA-core kernels.  The noise is keyed by the global row, so every range equals the same rows generated by
+    hand; a row's arithmetic in the tensor-core kernel does not depend on its batch (bit-equal against a 200-row launch)."""
+    eng, _ = engine_for('ckpt')
+    mels = synth.synth_mels(77, 300, 21)
+    steps = 500
+    a = eng.generate(mels[:256], seed=9, max_steps=steps, want_wave=False)
+    assert eng.last_kernel() == 'wavernn_tc_kernel'
+    la = a['labels'].cpu().numpy()[:, :steps]
+    b = eng.generate(mels[:200], seed=9, max_steps=steps, want_wave=False, kernel='tc')['labels'].cpu().numpy()[:, :steps]
+    assert np.array_equal(la[:200], b)
+    small = eng.generate(mels[:100], seed=9, max_steps=steps, want_wave=False)
+    assert eng.last_kernel() == 'wavernn_grid_kernel'
+    full = eng.generate(mels, seed=9, max_steps=steps, want_wave=False)['labels'].cpu().numpy()[:, :steps]
+    assert np.array_equal(full[:256], la)
+    tail = eng.generate(mels[256:], seed=9, utterance_offset=256, max_steps=steps, want_wave=False)['labels'].cpu().numpy()[:, :steps]
+    assert np.array_equal(full[256:], tail)
+    # the CUDA-core and the tensor-core kernel draw the same labels up to sampling near-ties (which then diverge the row)
+    same = (small['labels'].cpu().numpy()[:, :50] == la[:100, :50]).all(axis=1).mean()
+    assert same >= 0.9, f'only {same:.2f} of the rows agree between the wide and the tensor-core kernel over 50 steps'
+
+
 def test_packed_rows_equal_standalone_utterances(torch_cuda):
     """Packed generation of a ragged set (gen_opts.d_pack_*): 2 / 8 kernel rows each run a queue of utterances back to back and
     restart from the zero state at every utterance start.  Every utterance must come out BIT FOR BIT as from a stand-alone run
