@@ -977,6 +977,7 @@ static void launch_tc(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cud
   a.teacher = ua.teacher; a.logits_out = ua.logits_out; a.labels = ua.labels;
   a.prof = nullptr;
   const bool prof = getenv("B200TTS_TC_PROF") != nullptr;
+  a.prof_mode = prof ? atoi(getenv("B200TTS_TC_PROF")) : 0;
   if (prof) {
     ctx->push_prof.ensure((size_t)kTcCtas * 12 * sizeof(long long));
     B200_CUDA(cudaMemsetAsync(ctx->push_prof.p, 0, (size_t)kTcCtas * 12 * sizeof(long long), st));
@@ -1001,6 +1002,20 @@ static void launch_tc(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cud
                                     "epi:tmem", "epi:math+store", "epi:publish", "cond:wait", "cond:compute"};
     static const char* roles[5] = {"GRU1", "GRU2", "fc1", "fc2", "fc3"};
     const int lo[6] = {0, 32, 96, 112, 128, 144};
+    if (a.prof_mode == 2 && ua.steps > 2) {    // chain events of group 0 (first CTA of every role), mean ns between consecutive events
+      const double n = (double)(ua.steps - 1);
+      auto ev = [&](int cta, int slot) { return (double)h[(size_t)cta * 12 + slot] / n; };
+      const double a0 = ev(0, 5), b0 = ev(0, 6), a2 = ev(0, 7);
+      double prev = b0;
+      fprintf(stderr, "tc chain (ns, group 0): GRU1 winners->published %.0f", b0 - a0);
+      for (int r = 1; r < 5; ++r) {
+        const double c0 = ev(lo[r], 0), d0 = ev(lo[r], 5), e0 = ev(lo[r], 6);
+        fprintf(stderr, " | hop %.0f  %s GEMM %.0f (first stage %.0f, last stage %.0f, last MMA issued %.0f, accumulator seen %.0f) epilogue %.0f", c0 - prev,
+                roles[r], d0 - c0, ev(lo[r], 2) - c0, ev(lo[r], 3) - c0, ev(lo[r], 4) - c0, d0 - c0, e0 - d0);
+        prev = e0;
+      }
+      fprintf(stderr, " | hop %.0f  (step %.0f)\n", a2 - prev, a2 - a0);
+    } else
     for (int r = 0; r < 5; ++r) {
       fprintf(stderr, "tc prof %-4s (cycles per lock-step):", roles[r]);
       for (int i = 0; i < 12; ++i) {

@@ -76,6 +76,7 @@ struct TcArgs {
   float* logits_out;             // [S][B][NC]
   int16_t* labels;               // [B][S]
   long long* prof;               // optional [144][12] cycle accounting
+  int prof_mode;                 // 1: cycles per role and activity; 2: globaltimer sums of the chain events of group 0 (launch_tc prints both)
 };
 
 // ---- small PTX wrappers ------------------------------------------------------------------------------------------------
@@ -337,9 +338,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
 #pragma unroll
   for (int i = 0; i < 12; ++i) pacc[i] = 0;
   long long tlast = clock64();
+#define TC_GT(slot, cond)                                                          \
+  do {                                                                             \
+    if (A.prof_mode == 2 && (cond)) {                                              \
+      unsigned long long gt_;                                                      \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                      \
+      pacc[slot] += (long long)gt_;                                                \
+    }                                                                              \
+  } while (0)
 #define TC_MARK(slot)                        \
   do {                                       \
-    if (A.prof) {                            \
+    if (A.prof && A.prof_mode != 2) {        \
       const long long now_ = clock64();      \
       pacc[slot] += now_ - tlast;            \
       tlast = now_;                          \
@@ -366,6 +375,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
             tc_job(R.role, j, v, cw, nprod);
             if (!tc_cnt_wait(counter(g, cw), (unsigned)nprod * (unsigned)(t + 1), pg)) break;
             TC_MARK(0);
+            TC_GT(0, j == 0 && g == 0 && t >= 1);
             asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores of the producers -> this thread's async-proxy reads
             const uint8_t* src = vec_img(v, g, t & 1);
             for (int ks = 0; ks < kTcStagesPerVec; ++ks, ++s) {
@@ -405,6 +415,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
               const unsigned sl = s % (unsigned)R.nstage, su = s / (unsigned)R.nstage;
               if (!tc_mbar_wait(&bar_full[sl], su & 1u, pg)) break;
               TC_MARK(3);
+              TC_GT(2, ks == 0 && j == 0 && g == 0 && t >= 1);
+              TC_GT(3, ks == kTcStagesPerVec - 1 && j == 0 && g == 0 && t >= 1);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const uint64_t dA = dA0 + (uint64_t)((sl * kTcStageBytes) >> 4);
 #pragma unroll
@@ -423,6 +435,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
             }
             if (pg.aborted) break;
             tc_commit(&bar_accfull[slot]);
+            TC_GT(4, j == 0 && g == 0 && t >= 1);
           }
       TC_FLUSH(2, 4);
     }
@@ -496,6 +509,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           if (t > 0) {
             tc_cnt_wait_warp(counter(g, TCN_W), 64u * (unsigned)t, pg, lane);
             TC_MARK(5);
+            TC_GT(5, g == 0 && t < A.steps);
+            TC_GT(7, g == 0 && t >= 2);
             const unsigned long long* wp = A.winners + ((((size_t)g * 2 + ((t - 1) & 1)) * kTcWinCopies + (R.ci & (kTcWinCopies - 1))) * kTcRows + row) * 16;
             unsigned long long best = 0ull;
 #pragma unroll
@@ -533,6 +548,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
 #pragma unroll
           for (int i = 0; i < U; i += 4) *reinterpret_cast<float4*>(xf + i) = make_float4(x1[i], x1[i + 1], x1[i + 2], x1[i + 3]);
           publish(g, TCN_C1, false);
+          TC_GT(6, g == 0 && t >= 1);
           // off the critical path: W_hh1 . h1(t) (the GEMM all GRU-1 CTAs start once h1(t) is complete) is moved from TMEM to
           // registers as soon as it is done, so that the gate math of step t+1 finds it there
           acc_wait(g);
@@ -575,19 +591,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
               cd[gate][0] = v.x; cd[gate][1] = v.y;
             }
           }
+          // own units of x1 (fp32).  Its counter was complete before this CTA's GEMM could even start (the loader waited for it), so
+          // the check costs one L2 round trip -- taken here, in the shadow of the GEMM, not after it
+          tc_cnt_wait_warp(counter(g, TCN_C1), (unsigned)(32 * 4 * kTcEW) * (unsigned)(t + 1), pg, lane);
+          const float2 xa = __ldcg(reinterpret_cast<const float2*>(A.x1f + (((size_t)g * 2 + (t & 1)) * kTcRows + row) * 512 + 8 * R.ci + u0));
+          const float x1[U] = {xa.x, xa.y};
           float gi[3][U];
           TC_MARK(8);
           acc_wait(2);
           TC_MARK(5);
+          TC_GT(5, g == 0 && t >= 1);
 #pragma unroll
           for (int gate = 0; gate < 3; ++gate) tc_readW<32, U>(tlane + 320u, gate * 8 + u0, gi[gate]);
           acc_release(2);
           TC_MARK(7);
-          // own units of x1 (fp32): the loader's acquire made x1 visible to the bulk copies; this thread needs its own
-          tc_cnt_wait_warp(counter(g, TCN_C1), (unsigned)(32 * 4 * kTcEW) * (unsigned)(t + 1), pg, lane);
-          TC_MARK(6);
-          const float2 xa = __ldcg(reinterpret_cast<const float2*>(A.x1f + (((size_t)g * 2 + (t & 1)) * kTcRows + row) * 512 + 8 * R.ci + u0));
-          const float x1[U] = {xa.x, xa.y};
           float hnew[U], x2[U];
 #pragma unroll
           for (int i = 0; i < U; ++i) {
@@ -600,6 +617,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           tc_storeW<U>(vec_img(TV_H2, g, t & 1), 8 * R.ci + u0, row, hnew);
           tc_storeW<U>(vec_img(TV_X2, g, t & 1), 8 * R.ci + u0, row, x2);
           publish(g, TCN_C2);
+          TC_GT(6, g == 0 && t >= 1);
           // off the critical path: W_hh2 . h2(t) from TMEM to registers for step t+1
           acc_wait(g);
           TC_MARK(6);
@@ -632,6 +650,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           TC_MARK(8);
           acc_wait(slot);
           TC_MARK(5);
+          TC_GT(5, g == 0 && t >= 1);
           float a[U];
           tc_readW<32, U>(tlane + (uint32_t)(slot * 160), u0, a);
           acc_release(slot);
@@ -640,6 +659,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           for (int i = 0; i < U; ++i) a[i] = fmaxf(a[i] + cd[i], 0.f);
           tc_storeW<U>(vec_img(vout, g, t & 1), 32 * R.ci + u0, row, a);
           publish(g, cout);
+          TC_GT(6, g == 0 && t >= 1);
         }
       }
     } else {
@@ -678,6 +698,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           TC_MARK(8);
           acc_wait(0);
           TC_MARK(5);
+          TC_GT(5, g == 0 && t >= 1);
           unsigned long long best = 0ull;
 #pragma unroll
           for (int hb = 0; hb < 2; ++hb) {
@@ -710,6 +731,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
             for (int cp = 0; cp < kTcWinCopies; ++cp)
               A.winners[((((size_t)g * 2 + (t & 1)) * kTcWinCopies + cp) * kTcRows + row) * 16 + R.ci] = best;
             publish(g, TCN_W);
+            TC_GT(6, g == 0 && t >= 1);
           }
           // (swin is rewritten only after the next accumulator wait, which follows this barrier in every thread's program order;
           //  the readers above finish before they arrive at the NEXT barrier, and writers of the next round pass THIS one first --
