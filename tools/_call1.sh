@@ -1,4 +1,8 @@
 set -x
 mkdir -p gpurun_out
+( timeout 900 python -m pytest tests/test_wavernn_gpu.py -q -x -k "test_tc_ or auto_dispatch" ) > gpurun_out/r02_tc_tests.log 2>&1
+tail -3 gpurun_out/r02_tc_tests.log
 ( timeout 300 env B200TTS_TC_PROF=2 python tools/quick_time.py tc 256 3000 ) > gpurun_out/r02_tc_chain.log 2>&1
-tail -3 gpurun_out/r02_tc_chain.log
+grep "tc chain" gpurun_out/r02_tc_chain.log | tail -1
+( timeout 300 python tools/quick_time.py tc 128,256 3000 ) > gpurun_out/r02_tc_time.log 2>&1
+tail -2 gpurun_out/r02_tc_time.log
