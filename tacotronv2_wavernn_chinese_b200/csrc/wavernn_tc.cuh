@@ -18,18 +18,25 @@
 // accumulator; the four chunk accumulators and the cross-term accumulator are added in fp32 registers (round to nearest).
 // CPU model of exactly this arithmetic: 2.6e-7 of max|out| against float64 where an fp32 FMA loop has 8.1e-7.
 //
-// DATA FLOW.  A producer thread owns one batch row (its TMEM lane) and the CTA's units: it reads its accumulators with
-// tcgen05.ld, does the gate math, and stores the result ALREADY SPLIT and ALREADY in the UMMA canonical layout into the
-// vector's image in global memory (L2): [K/32 stages][plane][k-step][k half][16 row groups][8 rows][8 halves] -- a warp's
-// stores are 512 contiguous bytes.  After a block barrier one thread releases a per-(vector, group) arrival counter
-// (red.release.gpu).  A consumer CTA's loader thread spins on the counter (ld.acquire.gpu), then streams the 256 KB image
-// through a ring of 16 KB shared-memory stages with cp.async.bulk; the MMA thread multiplies stage by stage and commits to
-// mbarriers.  Vectors are double-buffered by step parity; the dependency chain of the recurrence itself guarantees that a
-// buffer is rewritten only after every reader of its previous content has finished.
+// DATA FLOW.  An epilogue thread owns one batch row (its TMEM lane) and a quarter of the CTA's columns (16 epilogue warps, 4 threads
+// per row): it reads its accumulators with tcgen05.ld, does the gate math, and stores the result ALREADY SPLIT and ALREADY in the
+// UMMA canonical layout into the vector's image in global memory (L2): [K/32 stages][plane][k-step][k half][16 row groups][8 rows]
+// [8 halves] -- rows of a warp are contiguous.  Every epilogue warp then releases one arrival on the per-(vector, group) counter
+// (red.release.gpu, cumulative over the warp barrier; no block barrier on the critical path).  A consumer CTA's loader thread spins
+// on the counter (ld.acquire.gpu), executes fence.proxy.async, and streams the 256 KB image through a ring of 16 KB shared-memory
+// stages with cp.async.bulk; the MMA thread issues six tcgen05.mma per stage and commits to the stage's mbarrier.  Vectors are
+// double-buffered by step parity; the dependency chain of the recurrence itself guarantees that a buffer is rewritten only after
+// every reader of its previous content has finished.
 //
-// What stays off the tensor cores, as in the push kernels (wavernn_push.cuh): the conditioning (per-frame tables, FIR
-// linearity), the sampled-label column of the I layer / GRU-1 (rank 1), the Gumbel-max race.  W_hh1.h1(t) and W_hh2.h2(t)
-// run one step ahead in the shadow of the other layers and wait in TMEM until the gate math of step t+1 reads them.
+// What stays off the tensor cores, as in the push kernels (wavernn_push.cuh): the conditioning (per-frame tables, FIR linearity;
+// GRU-1's 64 values per row come from 4 dedicated warps in blocks of <= 8 steps through a ring in L2), the sampled-label column of
+// the I layer / GRU-1 (rank 1), the Gumbel-max race.  W_hh1.h1(t) and W_hh2.h2(t) run one step ahead in the shadow of the other
+// layers and are moved from TMEM to registers as soon as they finish.  Every wait is bounded (PollGuard, ~2 s) and raises the
+// launch's error flag instead of hanging.
+//
+// Measured (B200): 50 us per lock-step for 128 as for 256 rows -- a latency chain: four GEMM phases of ~7.7 us each (the arrival
+// of the image, ~20 bytes per clock and SM; in isolation the same ring runs at 80-124, tools/bulk_stream_bench.cu), gate math
+// 1.4-3.9 us per layer, exchanges 0.5-4.4 us.  B200TTS_TC_PROF=1 / 2 print the cycle accounting / the chain link by link.
 #pragma once
 #include <cuda_fp16.h>
 #include "common.cuh"

@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests -q -x -m gpu ) > gpurun_out/r02_gpu_suite_final.log 2>&1
-tail -4 gpurun_out/r02_gpu_suite_final.log
-( timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" ) > gpurun_out/r02_smoke_final.log 2>&1
-tail -2 gpurun_out/r02_smoke_final.log
+( timeout 600 python -m pytest tests/test_wavernn_gpu.py -q -x -k "test_tc_ or auto_dispatch" ) > gpurun_out/r02_tc_tests.log 2>&1
+tail -2 gpurun_out/r02_tc_tests.log
+( timeout 200 python tools/quick_time.py tc 128,256 3000 ) > gpurun_out/r02_tc_time.log 2>&1
+tail -2 gpurun_out/r02_tc_time.log
