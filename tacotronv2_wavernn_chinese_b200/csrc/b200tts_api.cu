@@ -978,6 +978,12 @@ static void launch_tc(b200tts_wavernn* ctx, const float* d_mel, GenArgs& ua, cud
   a.prof = nullptr;
   const bool prof = getenv("B200TTS_TC_PROF") != nullptr;
   a.prof_mode = prof ? atoi(getenv("B200TTS_TC_PROF")) : 0;
+#ifndef B200TTS_TC_CHAIN_PROF
+  if (a.prof_mode == 2) {      // the chain-event probe is a compile-time option (wavernn_tc.cuh): fall back to the cycle accounting
+    fprintf(stderr, "libb200tts: B200TTS_TC_PROF=2 needs a build with -DB200TTS_TC_CHAIN_PROF; printing the cycle accounting instead\n");
+    a.prof_mode = 1;
+  }
+#endif
   if (prof) {
     ctx->push_prof.ensure((size_t)kTcCtas * 12 * sizeof(long long));
     B200_CUDA(cudaMemsetAsync(ctx->push_prof.p, 0, (size_t)kTcCtas * 12 * sizeof(long long), st));

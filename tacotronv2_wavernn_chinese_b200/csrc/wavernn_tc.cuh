@@ -36,7 +36,8 @@
 //
 // Measured (B200): 50 us per lock-step for 128 as for 256 rows -- a latency chain: four GEMM phases of ~7.7 us each (the arrival
 // of the image, ~20 bytes per clock and SM; in isolation the same ring runs at 80-124, tools/bulk_stream_bench.cu), gate math
-// 1.4-3.9 us per layer, exchanges 0.5-4.4 us.  B200TTS_TC_PROF=1 / 2 print the cycle accounting / the chain link by link.
+// 1.4-3.9 us per layer, exchanges 0.5-4.4 us.  B200TTS_TC_PROF=1 prints the cycle accounting; = 2, in a build with
+// -DB200TTS_TC_CHAIN_PROF, the chain link by link.
 #pragma once
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -345,6 +346,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
 #pragma unroll
   for (int i = 0; i < 12; ++i) pacc[i] = 0;
   long long tlast = clock64();
+// chain-event probe (B200TTS_TC_PROF=2): compiled in only with -DB200TTS_TC_CHAIN_PROF -- even when switched off at run time its
+// predicates on the critical path cost 2 % of a lock-step (52.2 -> 53.3 us, same box: profiles/r02_tc_ab_variants.txt)
+#ifdef B200TTS_TC_CHAIN_PROF
 #define TC_GT(slot, cond)                                                          \
   do {                                                                             \
     if (A.prof_mode == 2 && (cond)) {                                              \
@@ -353,9 +357,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
       pacc[slot] += (long long)gt_;                                                \
     }                                                                              \
   } while (0)
+#define TC_CYCLES_ON (A.prof && A.prof_mode != 2)
+#else
+#define TC_GT(slot, cond) do { } while (0)
+#define TC_CYCLES_ON (A.prof)
+#endif
 #define TC_MARK(slot)                        \
   do {                                       \
-    if (A.prof && A.prof_mode != 2) {        \
+    if (TC_CYCLES_ON) {                      \
       const long long now_ = clock64();      \
       pacc[slot] += now_ - tlast;            \
       tlast = now_;                          \
@@ -598,11 +607,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
               cd[gate][0] = v.x; cd[gate][1] = v.y;
             }
           }
-          // own units of x1 (fp32).  Its counter was complete before this CTA's GEMM could even start (the loader waited for it), so
-          // the check costs one L2 round trip -- taken here, in the shadow of the GEMM, not after it
-          tc_cnt_wait_warp(counter(g, TCN_C1), (unsigned)(32 * 4 * kTcEW) * (unsigned)(t + 1), pg, lane);
-          const float2 xa = __ldcg(reinterpret_cast<const float2*>(A.x1f + (((size_t)g * 2 + (t & 1)) * kTcRows + row) * 512 + 8 * R.ci + u0));
-          const float x1[U] = {xa.x, xa.y};
           float gi[3][U];
           TC_MARK(8);
           acc_wait(2);
@@ -612,6 +616,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) wavernn_tc_kernel(TcArgs A) {
           for (int gate = 0; gate < 3; ++gate) tc_readW<32, U>(tlane + 320u, gate * 8 + u0, gi[gate]);
           acc_release(2);
           TC_MARK(7);
+          // own units of x1 (fp32).  Its counter was complete before this CTA's GEMM could even start (the loader waited for it), so the
+          // check passes at its first poll.  It stays AFTER the accumulator read: polled before the accumulator wait (in the shadow of
+          // the GEMM) the 64 x 16 warps' acquire loads compete with the bulk-copy stream and the step gets 0.8 us longer (same box A/B)
+          tc_cnt_wait_warp(counter(g, TCN_C1), (unsigned)(32 * 4 * kTcEW) * (unsigned)(t + 1), pg, lane);
+          const float2 xa = __ldcg(reinterpret_cast<const float2*>(A.x1f + (((size_t)g * 2 + (t & 1)) * kTcRows + row) * 512 + 8 * R.ci + u0));
+          const float x1[U] = {xa.x, xa.y};
           float hnew[U], x2[U];
 #pragma unroll
           for (int i = 0; i < U; ++i) {
