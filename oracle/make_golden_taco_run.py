@@ -1,0 +1,99 @@
+"""WHOLE-RUN golden for the Tacotron-2 decoder, produced by driving the reference's own serialized decoder-step graph through
+the complete sentence (config 4: train.txt line 241, ~400 steps) -- container only (needs /root/reference).
+
+TEST INFRASTRUCTURE.  oracle/make_golden_taco_step.py pins single steps from states the restatement itself produced; here the
+loop state is carried from graph step to graph step, so the restatement's whole trajectory (every frame, every alignment, the
+stop step) is compared with a trajectory that never passes through oracle.tacotron_oracle.decoder_step.  All per-step arithmetic
+is the serialized `decoder/while/CustomDecoderStep/*` sub-graph evaluated by oracle/tf_graph_eval.py on the shipped checkpoint.
+The glue between two steps is the inference loop's own and is pinned separately by executing the reference's classes:
+  * zoneout at inference, state <- 0.9 new + 0.1 previous (modules.py:137-138; tests/test_tacotron_graph_pins.py runs
+    ZoneoutLSTMCell itself) -- the serialized graph is the TRAINING graph, so this line is applied here, outside it;
+  * next input = the frame just produced, stop when round(sigmoid(stop logit)) == 1 (helpers.py:42-66; TacoTestHelper itself
+    is executed in the same test file);
+  * initial state (attention.py:112-117, helpers.py:149).
+The prenet keep-masks are the ones oracle.decode draws for seed 1238 (RandomState stream, [steps, 2, 256]).
+
+    python oracle/make_golden_taco_run.py        ->  tests/golden/taco_run_from_graph.npz
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import tacotron_oracle as to                               # noqa: E402
+import tf_graph_eval as E                                   # noqa: E402
+from make_golden_taco_graph import DEFAULT_META            # noqa: E402
+from make_golden_taco_step import CKPT_DIR, run_graph_step  # noqa: E402
+from tacotronv2_wavernn_chinese_b200.tacotron import ckpt  # noqa: E402
+
+F32 = np.float32
+SEED = 1238
+MAX_ITERS = 700
+
+
+def drive_graph(nodes, variables, memory, keys, masks, zoneout=0.1, max_iters=MAX_ITERS):
+    Tx, U = memory.shape[0], 256
+    z = F32(zoneout)
+    zeros = np.zeros((1, U), dtype=F32)
+    alpha0 = np.zeros(Tx, dtype=F32)
+    alpha0[0] = 1
+    st = dict(c1=zeros, h1=zeros, c2=zeros, h2=zeros, ctx=np.zeros((1, memory.shape[1]), dtype=F32), alpha=alpha0, cum=alpha0.copy(),
+              mu=F32(0.5))
+    x = np.zeros((1, 80), dtype=F32)
+    frames, stops, aligns = [], [], []
+    zoned = lambda new, prev: ((F32(1) - z) * new + z * prev).astype(F32)
+    for step in range(max_iters):
+        g = run_graph_step(nodes, variables, memory, keys, x, masks[step].astype(F32), st)
+        st = dict(c1=zoned(g['new_c1'], st['c1']), h1=zoned(g['new_h1'], st['h1']), c2=zoned(g['new_c2'], st['c2']),
+                  h2=zoned(g['new_h2'], st['h2']), ctx=np.asarray(g['context'], dtype=F32).reshape(1, -1),
+                  alpha=np.asarray(g['alignments'], dtype=F32).reshape(-1), cum=np.asarray(g['cum'], dtype=F32).reshape(-1),
+                  mu=F32(np.asarray(g['mu']).reshape(-1)[0]))
+        frame = np.asarray(g['frame'], dtype=F32).reshape(1, 80)
+        logit = F32(np.asarray(g['stop_logit']).reshape(-1)[0])
+        stop = F32(1) / (F32(1) + np.exp(-logit, dtype=F32))
+        frames.append(frame[0]); stops.append(stop); aligns.append(st['alpha'].copy())
+        x = frame
+        if stop > 0.5:
+            break
+    return np.stack(frames), np.array(stops, dtype=F32), np.stack(aligns)
+
+
+def main():
+    nodes = E.load_graph(DEFAULT_META)
+    variables = ckpt.load_bundle(CKPT_DIR)
+    w = ckpt.load_tacotron_weights(CKPT_DIR)
+    sent = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'taco_symbols.json')))['sentences']['241']
+    ids = np.array(sent['ids'])
+    memory = to.encoder(w, ids)
+    keys = (memory @ w['memory_layer/kernel']).astype(F32)
+    masks = (np.random.RandomState(SEED).uniform(size=(MAX_ITERS, 2, 256)) >= 0.5)      # the stream oracle.decode(seed=SEED) draws
+    t0 = time.time()
+    frames, stops, aligns = drive_graph(nodes, variables, memory, keys, masks)
+    n = len(frames)
+    print(f'graph-driven run: {n} steps in {time.time() - t0:.1f} s')
+    d = to.decode(w, memory, dropout_masks=masks.astype(F32), max_iters=MAX_ITERS)
+    print('oracle run:', d['n_steps'], 'steps')
+    m = min(n, d['n_steps'])
+    err = np.abs(d['frames'][:m] - frames[:m]).max(axis=1)
+    for s in (0, 10, 50, 100, 200, 300, m - 1):
+        if s < m:
+            print(f'  step {s:4d}: max |frame diff| {err[s]:.3e}')
+    print('  overall', float(err.max()), ' alignment argmax identical:', bool((d['alignments'][:m].argmax(1) == aligns[:m].argmax(1)).all()))
+    path = os.path.join(ROOT, 'tests', 'golden', 'taco_run_from_graph.npz')
+    np.savez_compressed(path, ids=ids, seed=np.array(SEED), n_steps=np.array(n), frames=frames, stop=stops,
+                        align_argmax=aligns.argmax(1).astype(np.int16), align_peak=aligns.max(1).astype(F32),
+                        masks=np.packbits(masks[:n].reshape(n, -1), axis=1))
+    print(f'wrote {path} ({os.path.getsize(path)} bytes)')
+
+
+if __name__ == '__main__':
+    main()

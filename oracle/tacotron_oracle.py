@@ -9,8 +9,12 @@ epsilon 1e-3 with moving statistics; `tf.layers.conv1d` 'same' cross-correlation
 *** Pinning status: the DECODER STEP (rows a-7, a-8 of SURVEY section 8: prenet, both LSTM cells, forward attention,
 projections), the ENCODER (convolution blocks, single BiLSTM iterations, the fw/bw wiring) and the POSTNET are pinned
 numerically AND structurally against the reference's own serialized graph, executed op by op in numpy on the shipped
-weights.  What has no reference vectors: whole-utterance TensorFlow outputs (the decoder loop iterated, with TF's own
-random masks). ***  Pins that ARE checked:
+weights, and the WHOLE decoder run of a sentence (405 steps of config 4) is pinned against the trajectory obtained by carrying
+the loop state through that serialized step graph from the first step to the stop token (bit-identical).  What has no
+reference vectors: outputs of a TensorFlow session itself (TF's own random masks). ***  Pins that ARE checked:
+  * tests/test_tacotron_run_pins.py: `decode` reproduces every frame, every attended position and the stop step of the
+    whole-sentence trajectory driven through the serialized graph (oracle/make_golden_taco_run.py ->
+    tests/golden/taco_run_from_graph.npz; measured difference 0.0 over 405 steps);
   * tests/test_tacotron_window_pins.py: the attention step WITH the optional inference window (row a-9) against the reference's
     own `ForwardLocationSensitiveAttention.__call__` (forward_attention.py:119-231), whose statements are executed unmodified
     on numpy arrays through a stand-in for the few tensorflow ops they use (oracle/ref_harness_taco_attention.py ->

@@ -1,6 +1,6 @@
 """sm_100a Tacotron-2 decoder loop (taco_decoder_kernel, through the C ABI) against the oracle with shared dropout masks.
-The oracle's decoder step is pinned against the reference's serialized graph (tests/test_tacotron_step_pins.py); whole-run
-TF outputs do not exist (see oracle/tacotron_oracle.py).  Tolerance from the north star: mel within 1e-4 abs, identical stop step."""
+The oracle's decoder step AND its whole 405-step run of config 4 are pinned against the reference's serialized graph
+(tests/test_tacotron_step_pins.py, tests/test_tacotron_run_pins.py; see oracle/tacotron_oracle.py).  Tolerance from the north star: mel within 1e-4 abs, identical stop step."""
 import numpy as np
 import pytest
 
