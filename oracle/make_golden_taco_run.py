@@ -33,6 +33,7 @@ import tacotron_oracle as to                               # noqa: E402
 import tf_graph_eval as E                                   # noqa: E402
 from make_golden_taco_graph import DEFAULT_META            # noqa: E402
 from make_golden_taco_step import CKPT_DIR, run_graph_step  # noqa: E402
+from make_golden_taco_encpost import ENC, POST, P, encoder_lstm_step, inference_feeds   # noqa: E402
 from tacotronv2_wavernn_chinese_b200.tacotron import ckpt  # noqa: E402
 
 F32 = np.float32
@@ -67,6 +68,33 @@ def drive_graph(nodes, variables, memory, keys, masks, zoneout=0.1, max_iters=MA
     return np.stack(frames), np.array(stops, dtype=F32), np.stack(aligns)
 
 
+def encoder_through_graph(nodes, variables, ids, zoneout=0.1):
+    """The whole encoder of one sentence: conv blocks as serialized (inference feeds), then the two LSTM loop bodies iterated
+    over all tokens with the inference zoneout between iterations (modules.py:137-138); the un-zoned h is the output (:142)."""
+    feeds = inference_feeds(variables, ENC)
+    feeds['datafeeder/input_queue_Dequeue'] = ids[None].astype(np.int32)
+    x = np.asarray(E.Evaluator(nodes, variables, feeds).get(P + ENC[-1] + 'batch_normalization/batchnorm/add_1')[0], dtype=F32)
+    Tx = x.shape[0]
+    z = F32(zoneout)
+    outs = []
+    for direction, order in (('fw', range(Tx)), ('bw', range(Tx - 1, -1, -1))):
+        c = h = np.zeros((1, 256), dtype=F32)
+        o = np.zeros((Tx, 256), dtype=F32)
+        for t in order:
+            nc, nh = encoder_lstm_step(nodes, variables, direction, x[t:t + 1], c, h)
+            nc, nh = np.asarray(nc, dtype=F32).reshape(1, -1), np.asarray(nh, dtype=F32).reshape(1, -1)
+            o[t] = nh[0]
+            c, h = ((F32(1) - z) * nc + z * c).astype(F32), ((F32(1) - z) * nh + z * h).astype(F32)
+        outs.append(o)
+    return np.concatenate(outs, axis=1).astype(F32)
+
+
+def postnet_through_graph(nodes, variables, frames):
+    feeds = inference_feeds(variables, POST)
+    feeds[P + 'Reshape_3'] = frames[None]                                                # decoder output, before the clip
+    return np.asarray(E.Evaluator(nodes, variables, feeds).get(P + 'Minimum_1')[0], dtype=F32)
+
+
 def main():
     nodes = E.load_graph(DEFAULT_META)
     variables = ckpt.load_bundle(CKPT_DIR)
@@ -88,8 +116,13 @@ def main():
         if s < m:
             print(f'  step {s:4d}: max |frame diff| {err[s]:.3e}')
     print('  overall', float(err.max()), ' alignment argmax identical:', bool((d['alignments'][:m].argmax(1) == aligns[:m].argmax(1)).all()))
+    # the run-once neighbours over the whole sentence: encoder (all 51 tokens through both LSTM loop bodies), postnet (all frames)
+    mem_g = encoder_through_graph(nodes, variables, ids)
+    mel_g = postnet_through_graph(nodes, variables, frames)
+    print(f'  encoder memory: graph vs oracle {np.abs(mem_g - memory).max():.3e} (max |memory| {np.abs(mem_g).max():.2f});'
+          f'  postnet mel: {np.abs(mel_g - to.postnet(w, frames)).max():.3e} (max |mel| {np.abs(mel_g).max():.2f})')
     path = os.path.join(ROOT, 'tests', 'golden', 'taco_run_from_graph.npz')
-    np.savez_compressed(path, ids=ids, seed=np.array(SEED), n_steps=np.array(n), frames=frames, stop=stops,
+    np.savez_compressed(path, memory_graph=mem_g, mel_graph=mel_g, ids=ids, seed=np.array(SEED), n_steps=np.array(n), frames=frames, stop=stops,
                         align_argmax=aligns.argmax(1).astype(np.int16), align_peak=aligns.max(1).astype(F32),
                         masks=np.packbits(masks[:n].reshape(n, -1), axis=1))
     print(f'wrote {path} ({os.path.getsize(path)} bytes)')

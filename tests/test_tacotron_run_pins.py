@@ -71,3 +71,19 @@ def test_whole_run_fixture_is_sensitive():
         warnings.simplefilter('ignore', RuntimeWarning)
         d = to.decode(w, memory, dropout_masks=masks, max_iters=60, zoneout=0.0)
     assert np.abs(d['frames'][:60] - z['frames'][:60]).max() > 1e-2
+
+
+def test_whole_encoder_and_whole_postnet_through_the_graph():
+    """The run-once neighbours over the WHOLE sentence: all 51 tokens through both serialized encoder-LSTM loop bodies (inference
+    zoneout between iterations), all 405 decoder frames through the serialized postnet (measured 3.9e-7 / 9.5e-7 absolute)."""
+    w = real_taco_weights()
+    if w is None:
+        pytest.skip('shipped Tacotron checkpoint not available on this box')
+    z, n, _ = _fixture()
+    mem = to.encoder(w, z['ids'])
+    assert mem.shape == z['memory_graph'].shape == (len(z['ids']), 512)
+    assert np.abs(mem - z['memory_graph']).max() <= 2e-6 * max(1.0, float(np.abs(z['memory_graph']).max()))
+    mel = to.postnet(w, z['frames'])
+    assert mel.shape == z['mel_graph'].shape == (n, 80)
+    assert np.abs(mel - z['mel_graph']).max() <= 2e-6 * max(1.0, float(np.abs(z['mel_graph']).max()))
+    assert z['mel_graph'].min() >= -4.1 - 1e-6 and z['mel_graph'].max() <= 4.0 + 1e-6          # tacotron.py:126-129 clip
