@@ -121,7 +121,7 @@ def load_weights(which):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arms.  kind "_ref": the UNMODIFIED reference WaveRNN.generate (fatchord_version.py:169), imported from the git-ignored
+# CPU arms.  kind "reference" (source oracle/_ref): the UNMODIFIED reference WaveRNN.generate (fatchord_version.py:169), imported from the git-ignored
 # travel copy oracle/_ref/reference_src.zip through oracle/ref_harness.py, shipped checkpoint, torch CPU.
 # kind "port": the numpy oracle port (oracle/wavernn_oracle.py), kept beside it for continuity with round 1.
 # ------------------------------------------------------------------------------------------------
@@ -244,7 +244,7 @@ def cpu_baseline(batch, frames, seconds):
     """cpu_baseline object of the b200 line / the reference arm: `_ref` when the travel copy is there, the port otherwise."""
     if ref_model() is not None:
         r = ref_sample(batch, seconds)
-        out = {'value': r['value'], 'unit': 'samples/s', 'cores': r['threads'], 'kind': '_ref',
+        out = {'value': r['value'], 'unit': 'samples/s', 'cores': r['threads'], 'kind': 'reference', 'source': 'oracle/_ref',
                'sample': f"{batch} utterances x {r['steps']} of {frames * HOP} lock-steps of the UNMODIFIED reference "
                          f"WaveRNN.generate loop (fatchord_version.py:201-241, shipped checkpoint, torch CPU, {r['threads']} intra-op "
                          f"threads picked by probe on a {os.cpu_count()}-thread host); the one-shot conditioning network is "

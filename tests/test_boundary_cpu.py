@@ -192,7 +192,7 @@ def test_fold_geometry_matches_reference_formula():
 
 def test_bench_cpu_arm_helpers():
     """bench.py's CPU arms (cpu_baseline / --impl reference): same config object as the GPU arm; a time-bounded sample of the
-    UNMODIFIED reference's generate loop when its travel copy is present (kind "_ref"), the numpy port beside it."""
+    UNMODIFIED reference's generate loop when its travel copy is present (kind "reference", source oracle/_ref), the numpy port beside it."""
     import argparse
     import bench
     args = argparse.Namespace(batch=4, frames=80)
@@ -208,7 +208,7 @@ def test_bench_cpu_arm_helpers():
         r = bench.ref_sample(4, 0.3)
         assert r['value'] > 0 and r['steps'] >= 8 and r['threads'] == 2
         base = bench.cpu_baseline(4, 80, 0.3)
-        assert base['kind'] == '_ref' and 'UNMODIFIED reference' in base['sample'] and base['port']['kind'] == 'port'
+        assert base['kind'] == 'reference' and base['source'] == 'oracle/_ref' and 'UNMODIFIED reference' in base['sample'] and base['port']['kind'] == 'port'
         torch.set_num_threads(min(4, torch.get_num_threads()))
 
 
