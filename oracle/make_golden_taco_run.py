@@ -39,6 +39,7 @@ from tacotronv2_wavernn_chinese_b200.tacotron import ckpt  # noqa: E402
 F32 = np.float32
 SEED = 1238
 MAX_ITERS = 700
+MORE = (('48', 11), ('42', 12))                  # (train.txt line, RandomState seed of the keep-masks): 17 and 52 tokens
 
 
 def drive_graph(nodes, variables, memory, keys, masks, zoneout=0.1, max_iters=MAX_ITERS):
@@ -126,6 +127,22 @@ def main():
                         align_argmax=aligns.argmax(1).astype(np.int16), align_peak=aligns.max(1).astype(F32),
                         masks=np.packbits(masks[:n].reshape(n, -1), axis=1))
     print(f'wrote {path} ({os.path.getsize(path)} bytes)')
+    # two more sentences of other lengths (the shortest and the longest of train.txt 1-64), other mask streams: trajectories only
+    more = {}
+    for key, seed in MORE:
+        ids2 = np.array(json.load(open(os.path.join(ROOT, 'tests', 'golden', 'taco_symbols.json')))['sentences'][key]['ids'])
+        mem2 = to.encoder(w, ids2)
+        keys2 = (mem2 @ w['memory_layer/kernel']).astype(F32)
+        masks2 = (np.random.RandomState(seed).uniform(size=(MAX_ITERS, 2, 256)) >= 0.5)
+        f2, s2, a2 = drive_graph(nodes, variables, mem2, keys2, masks2)
+        d2 = to.decode(w, mem2, dropout_masks=masks2.astype(F32), max_iters=MAX_ITERS)
+        print(f'  sentence {key} ({len(ids2)} tokens, seed {seed}): graph {len(f2)} steps, oracle {d2["n_steps"]} steps, '
+              f'max |frame diff| {np.abs(d2["frames"][:len(f2)] - f2[:d2["n_steps"]]).max():.3e}')
+        more.update({f's{key}_ids': ids2, f's{key}_seed': np.array(seed), f's{key}_frames': f2, f's{key}_stop': s2,
+                     f's{key}_align_argmax': a2.argmax(1).astype(np.int16)})
+    path2 = os.path.join(ROOT, 'tests', 'golden', 'taco_run_from_graph_more.npz')
+    np.savez_compressed(path2, sentences=np.array([k for k, _ in MORE]), **more)
+    print(f'wrote {path2} ({os.path.getsize(path2)} bytes)')
 
 
 if __name__ == '__main__':
