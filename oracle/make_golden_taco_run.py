@@ -69,6 +69,55 @@ def drive_graph(nodes, variables, memory, keys, masks, zoneout=0.1, max_iters=MA
     return np.stack(frames), np.array(stops, dtype=F32), np.stack(aligns)
 
 
+def drive_graph_window(nodes, variables, w, memory, keys, masks, zoneout=0.1, max_iters=MAX_ITERS):
+    """The same loop with the optional INFERENCE WINDOW (SURVEY a-9), which the serialized graph does not contain: prenet, both LSTM
+    cells and the two projections come from the serialized step graph, the attention step -- forward recursion, window, context,
+    transition probability -- from the reference's OWN `ForwardLocationSensitiveAttention.__call__` (forward_attention.py:119-231)
+    executed on numpy arrays (oracle/ref_harness_taco_attention.py), whose context is fed back into the graph's projections."""
+    import ref_harness_taco_attention as R
+    from make_golden_taco_step import STEP, TARGETS, LOOP
+    att = R.ReferenceAttention(w, memory)
+    Tx = memory.shape[0]
+    z = F32(zoneout)
+    zeros = np.zeros((1, 256), dtype=F32)
+    alpha0 = np.zeros(Tx, dtype=F32)
+    alpha0[0] = 1
+    st = dict(c1=zeros, h1=zeros, c2=zeros, h2=zeros, ctx=np.zeros((1, memory.shape[1]), dtype=F32), alpha=alpha0, cum=alpha0.copy(),
+              mu=F32(0.5))
+    max_att, pos_rec = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    x = np.zeros((1, 80), dtype=F32)
+    frames, stops, aligns, maxes = [], [], [], []
+    zoned = lambda new, prev: ((F32(1) - z) * new + z * prev).astype(F32)
+    for step in range(max_iters):
+        m = masks[step].astype(F32)
+        g = run_graph_step(nodes, variables, memory, keys, x, m, st)                       # cells: independent of this step's attention
+        state = R.State(alignments=st['alpha'][None], cumulated_alignments=st['cum'][None], alpha=st['alpha'][None],
+                        mu=np.reshape(st['mu'], (1, 1)).astype(F32), max_attentions=max_att, pos_rec=pos_rec)
+        al, mu, ctx, cum, max_att, pos_rec = att(np.asarray(g['new_h2'], dtype=F32).reshape(1, -1), state)
+        max_att, pos_rec = np.asarray(max_att, np.int32).reshape(1), np.asarray(pos_rec, np.int32).reshape(1)
+        ctx = np.asarray(ctx, dtype=F32).reshape(1, -1)
+        # projections of [new_h2, context] as serialized, with the windowed context fed in place of the graph's own
+        feeds = {
+            LOOP + 'Identity_17': x, LOOP + 'Identity_4': st['c1'], LOOP + 'Identity_5': st['h1'], LOOP + 'Identity_6': st['c2'],
+            LOOP + 'Identity_7': st['h2'], LOOP + 'Identity_8': st['ctx'],
+            STEP + 'decoder_prenet/dropout_1decoder_prenet/dropout/Cast': m[0][None, :],
+            STEP + 'decoder_prenet/dropout_2decoder_prenet/dropout/Cast': m[1][None, :],
+            TARGETS['context']: ctx,
+        }
+        ev = E.Evaluator(nodes, variables, feeds)
+        frame = np.asarray(ev.get(TARGETS['frame']), dtype=F32).reshape(1, 80)
+        logit = F32(np.asarray(ev.get(TARGETS['stop_logit'])).reshape(-1)[0])
+        st = dict(c1=zoned(g['new_c1'], st['c1']), h1=zoned(g['new_h1'], st['h1']), c2=zoned(g['new_c2'], st['c2']),
+                  h2=zoned(g['new_h2'], st['h2']), ctx=ctx, alpha=np.asarray(al, dtype=F32).reshape(-1),
+                  cum=np.asarray(cum, dtype=F32).reshape(-1), mu=F32(np.asarray(mu).reshape(-1)[0]))
+        stop = F32(1) / (F32(1) + np.exp(-logit, dtype=F32))
+        frames.append(frame[0]); stops.append(stop); aligns.append(st['alpha'].copy()); maxes.append(int(max_att[0]))
+        x = frame
+        if stop > 0.5:
+            break
+    return np.stack(frames), np.array(stops, dtype=F32), np.stack(aligns), np.array(maxes, dtype=np.int16)
+
+
 def encoder_through_graph(nodes, variables, ids, zoneout=0.1):
     """The whole encoder of one sentence: conv blocks as serialized (inference feeds), then the two LSTM loop bodies iterated
     over all tokens with the inference zoneout between iterations (modules.py:137-138); the un-zoned h is the output (:142)."""
@@ -140,6 +189,14 @@ def main():
               f'max |frame diff| {np.abs(d2["frames"][:len(f2)] - f2[:d2["n_steps"]]).max():.3e}')
         more.update({f's{key}_ids': ids2, f's{key}_seed': np.array(seed), f's{key}_frames': f2, f's{key}_stop': s2,
                      f's{key}_align_argmax': a2.argmax(1).astype(np.int16)})
+    # config-4 sentence once more WITH the inference window
+    fw, sw, aw, mw = drive_graph_window(nodes, variables, w, memory, keys, masks)
+    dw = to.decode(w, memory, dropout_masks=masks.astype(F32), max_iters=MAX_ITERS, window=True)
+    mm = min(len(fw), dw['n_steps'])
+    print(f'  windowed run of sentence 241: graph + reference attention class {len(fw)} steps, oracle {dw["n_steps"]} steps, '
+          f'max |frame diff| {np.abs(dw["frames"][:mm] - fw[:mm]).max():.3e}; differs from the un-windowed run by '
+          f'{np.abs(fw[:min(len(fw), n)] - frames[:min(len(fw), n)]).max():.2f}')
+    more.update(w241_frames=fw, w241_stop=sw, w241_align_argmax=aw.argmax(1).astype(np.int16), w241_max_att=mw)
     path2 = os.path.join(ROOT, 'tests', 'golden', 'taco_run_from_graph_more.npz')
     np.savez_compressed(path2, sentences=np.array([k for k, _ in MORE]), **more)
     print(f'wrote {path2} ({os.path.getsize(path2)} bytes)')

@@ -14,7 +14,8 @@ the loop state through that serialized step graph from the first step to the sto
 reference vectors: outputs of a TensorFlow session itself (TF's own random masks). ***  Pins that ARE checked:
   * tests/test_tacotron_run_pins.py: `decode` reproduces every frame, every attended position and the stop step of the
     whole-sentence trajectory driven through the serialized graph (oracle/make_golden_taco_run.py ->
-    tests/golden/taco_run_from_graph.npz; measured difference 0.0 over 405 steps);
+    tests/golden/taco_run_from_graph.npz; measured difference 0.0 over 405 steps); the same for a 17-token and a 52-token sentence
+    and for the run WITH the inference window (418 steps; attention step = the reference's own class executed on numpy);
   * tests/test_tacotron_window_pins.py: the attention step WITH the optional inference window (row a-9) against the reference's
     own `ForwardLocationSensitiveAttention.__call__` (forward_attention.py:119-231), whose statements are executed unmodified
     on numpy arrays through a stand-in for the few tensorflow ops they use (oracle/ref_harness_taco_attention.py ->

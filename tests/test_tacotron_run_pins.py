@@ -113,3 +113,31 @@ def test_whole_run_other_sentence_lengths(key):
     assert d['n_steps'] == n and err.max() <= 1e-6
     assert np.array_equal(d['alignments'].argmax(1), z[f's{key}_align_argmax'])
     np.testing.assert_allclose(d['stop'], z[f's{key}_stop'], rtol=0, atol=1e-6)
+
+
+def test_whole_run_with_the_inference_window():
+    """Config-4 sentence WITH the optional inference window (SURVEY a-9; forward_attention.py:171-215), 418 steps: cells and
+    projections from the serialized graph, the attention step from the reference's OWN ForwardLocationSensitiveAttention.__call__
+    executed on numpy arrays, state carried from step to step (oracle/make_golden_taco_run.py: drive_graph_window)."""
+    w = real_taco_weights()
+    if w is None:
+        pytest.skip('shipped Tacotron checkpoint not available on this box')
+    z, n0, masks = _fixture()
+    zw = np.load(os.path.join(GOLDEN, 'taco_run_from_graph_more.npz'))
+    frames = zw['w241_frames']
+    n = frames.shape[0]
+    assert n == 418 and np.abs(frames[:n0] - z['frames'][:min(n, n0)]).max() > 1.0      # the window changes the trajectory
+    masks = (np.random.RandomState(int(z['seed'])).uniform(size=(700, 2, 256)) >= 0.5).astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)
+        d = to.decode(w, to.encoder(w, z['ids']), dropout_masks=masks, max_iters=700, window=True)
+    m = min(n, d['n_steps'])
+    err = np.abs(d['frames'][:m] - frames[:m]).max(axis=1)
+    assert err[:40].max() <= 1e-5
+    if err[:40].max() > 0:
+        assert abs(d['n_steps'] - n) <= 0.05 * n
+        return
+    assert d['n_steps'] == n and err.max() <= 1e-6
+    assert np.array_equal(d['alignments'].argmax(1), zw['w241_align_argmax'])
+    mx = zw['w241_max_att'].astype(int)
+    assert (np.diff(mx) >= 0).all() and (np.diff(mx) <= 1).all()                        # monotone, at most one token per step
