@@ -228,3 +228,50 @@ def test_reference_travel_copy_times_the_reference_loop():
     b = rh.timed_generate_sample(m, mel, max_steps=8)
     assert a['steps'] == b['steps'] == 8 and b['upsample_seconds'] < max(0.05, 0.5 * full['upsample_seconds'])
     assert m.training                                         # generate() leaves the module in train() mode (:262)
+
+
+def test_error_codes_and_messages_without_a_device():
+    """Status-code contract of include/b200tts.h: 0 / negative B200TTS_E* + a thread-local message, nothing throws across the ABI.
+    Argument checks come before any CUDA call, so they can be exercised on a box without a GPU."""
+    lib, L = _lib()
+    EINVAL, ECUDA = -1, -2
+    h = ctypes.c_void_p()
+    cfg = L.WaveRNNCfg()
+    assert lib.b200tts_wavernn_create(ctypes.byref(h), 0, ctypes.byref(cfg), None, 0) == EINVAL        # null weights
+    assert b'null argument' in lib.b200tts_last_error() and not h.value
+    dims = dict(synth_mod.DEFAULT_DIMS)
+    arr, keep = L.make_tensor_array({k: np.asarray(v, dtype=np.float32) for k, v in
+                                     wo.as_params(synth_mod.synth_state_dict(0)).items() if np.asarray(v).dtype.kind == 'f'})
+    from tacotronv2_wavernn_chinese_b200.engine import _cfg_from_dims
+    bad = _cfg_from_dims(dict(dims, upsample_factors=(5, 5, 10)))                                     # prod != hop_length
+    assert lib.b200tts_wavernn_create(ctypes.byref(h), 0, ctypes.byref(bad), arr, len(arr)) == EINVAL
+    assert b'hop_length' in lib.b200tts_last_error()
+    bad = _cfg_from_dims(dict(dims, bits=16))                                                         # labels are int16
+    assert lib.b200tts_wavernn_create(ctypes.byref(h), 0, ctypes.byref(bad), arr, len(arr)) == EINVAL
+    nf, fl = ctypes.c_int(), ctypes.c_int()
+    assert lib.b200tts_wavernn_fold_geometry(80, 275, 11000, 1, ctypes.byref(nf), ctypes.byref(fl)) == EINVAL   # overlap < 2
+    assert lib.b200tts_wavernn_fold_geometry(1, 275, 11000, 550, ctypes.byref(nf), ctypes.byref(fl)) == EINVAL  # shorter than the overlap
+    assert lib.b200tts_wavernn_generate(None, None, 1, 21, None, None, None, None, None) == EINVAL
+    assert lib.b200tts_wavernn_check(None) == EINVAL
+    assert lib.b200tts_wavernn_launch_count(None) == -1 and lib.b200tts_wavernn_last_kernel(None) == 0
+    lib.b200tts_wavernn_destroy(None)                                                                 # no-op, must not crash
+    import torch
+    if not torch.cuda.is_available():
+        good = _cfg_from_dims(dims)
+        rc = lib.b200tts_wavernn_create(ctypes.byref(h), 0, ctypes.byref(good), arr, len(arr))
+        assert rc == ECUDA and lib.b200tts_last_error() and not h.value                               # no device: loud, no fallback
+        v = ctypes.c_double()
+        assert lib.b200tts_debug_fp32_peak(0, ctypes.byref(v)) == ECUDA
+    del keep
+
+
+def test_taco_error_codes_without_a_device():
+    lib, L = _lib()
+    h = ctypes.c_void_p()
+    cfg = L.TacoCfg()
+    assert lib.b200tts_taco_create(ctypes.byref(h), 0, ctypes.byref(cfg), None, 0) == -1 and not h.value
+    assert lib.b200tts_last_error()
+    lib.b200tts_taco_destroy(None)
+    assert lib.b200tts_taco_decode(None, None, None, 1, 5, None, 10, 0, None, None, None, None, None) == -1
+    assert lib.b200tts_taco_encode(None, None, None, 1, 5, None, None) == -1
+    assert lib.b200tts_taco_postnet(None, None, None, 1, 10, None, None) == -1
